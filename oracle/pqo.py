@@ -1,0 +1,225 @@
+"""ctypes binding of the C oracle (oracle/pq_oracle.c).  TEST INFRASTRUCTURE ONLY.
+
+Columns are (values: float64 ndarray, ok: bool ndarray | None).  Every wrapper returns
+(values, ok) per output; null slots hold NaN.  Raises OracleError when the reference
+itself would fail on the input (PQO_ERR_*).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+_HERE = Path(__file__).resolve().parent
+_SO = _HERE / "libpq_oracle.so"
+
+ERRORS = {-1: "nulls (cont_slice Err)", -2: "reference panics", -3: "shape Err", -4: "alloc"}
+
+
+class OracleError(Exception):
+    def __init__(self, code):
+        super().__init__("oracle: reference would fail: %s" % ERRORS.get(code, code))
+        self.code = code
+
+
+def build(force: bool = False) -> Path:
+    src = _HERE / "pq_oracle.c"
+    if force or not _SO.exists() or _SO.stat().st_mtime < src.stat().st_mtime:
+        env = dict(os.environ)
+        env.setdefault("CC", "gcc")
+        subprocess.run(["make", "-C", str(_HERE), "-B", "libpq_oracle.so"], check=True, env=env,
+                       stdout=subprocess.DEVNULL)
+    return _SO
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(str(_SO))
+    return _lib
+
+
+class SuiteParams(C.Structure):
+    """Mirror of pqo_suite_params (== the defaults of the reference's Python signatures)."""
+    _fields_ = [("sma", C.c_int32), ("ema", C.c_int32), ("tema", C.c_int32), ("trima", C.c_int32),
+                ("bb", C.c_int32), ("bb_up", C.c_double), ("bb_dn", C.c_double),
+                ("macd_fast", C.c_int32), ("macd_slow", C.c_int32), ("macd_signal", C.c_int32),
+                ("rsi", C.c_int32), ("atr", C.c_int32), ("natr", C.c_int32),
+                ("stoch_k", C.c_int32), ("stoch_sk", C.c_int32), ("stoch_sd", C.c_int32),
+                ("willr", C.c_int32), ("midprice", C.c_int32)]
+
+    @classmethod
+    def default(cls):
+        return cls(30, 30, 30, 30, 20, 2.0, 2.0, 12, 26, 9, 14, 14, 14, 9, 3, 3, 14, 14)
+
+
+def _col(x, ok=None):
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    if ok is not None:
+        ok = np.ascontiguousarray(ok, dtype=np.uint8)
+        assert ok.shape == x.shape
+    return x, ok
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _outs(n, k):
+    return [(np.empty(n, np.float64), np.empty(n, np.uint8)) for _ in range(k)]
+
+
+def _ret(rc, outs):
+    if rc != 0:
+        raise OracleError(rc)
+    res = [(v, o.astype(bool)) for v, o in outs]
+    return res[0] if len(res) == 1 else tuple(res)
+
+
+def _call(name, cols, ints, n_out, floats=()):
+    """cols: list of (x, ok); ints: trailing int64 params; floats: trailing doubles after ints."""
+    f = getattr(lib(), name)
+    n = len(cols[0][0])
+    args = []
+    for x, ok in cols:
+        args += [_p(x), _p(ok)]
+    args.append(C.c_int64(n))
+    args += [C.c_int64(int(i)) for i in ints]
+    args += [C.c_double(float(d)) for d in floats]
+    outs = _outs(n, n_out)
+    for v, o in outs:
+        args += [_p(v), _p(o)]
+    f.restype = C.c_int
+    return _ret(f(*args), outs)
+
+
+def sma(x, p, ok=None): return _call("pqo_sma", [_col(x, ok)], [p], 1)
+def ema(x, p, ok=None): return _call("pqo_ema", [_col(x, ok)], [p], 1)
+def tema(x, p, ok=None): return _call("pqo_tema", [_col(x, ok)], [p], 1)
+def trima(x, p, ok=None): return _call("pqo_trima", [_col(x, ok)], [p], 1)
+def wma(x, p, ok=None): return _call("pqo_wma", [_col(x, ok)], [p], 1)
+def ma(x, p, matype=0, ok=None): return _call("pqo_ma", [_col(x, ok)], [p, matype], 1)
+def midpoint(x, p=14, ok=None): return _call("pqo_midpoint", [_col(x, ok)], [p], 1)
+def rsi(x, p=14, ok=None): return _call("pqo_rsi", [_col(x, ok)], [p], 1)
+def mom(x, p=10, ok=None): return _call("pqo_mom", [_col(x, ok)], [p], 1)
+def cmo(x, p=14, ok=None): return _call("pqo_cmo", [_col(x, ok)], [p], 1)
+
+
+def rma(x, p):
+    x, _ = _col(x)
+    n = len(x)
+    outs = _outs(n, 1)
+    f = lib().pqo_rma
+    f.restype = C.c_int
+    return _ret(f(_p(x), C.c_int64(n), C.c_int64(p), _p(outs[0][0]), _p(outs[0][1])), outs)
+
+
+def roc(x, p=10, kind=0, ok=None):
+    x, ok = _col(x, ok)
+    n = len(x)
+    outs = _outs(n, 1)
+    f = lib().pqo_roc
+    f.restype = C.c_int
+    return _ret(f(_p(x), _p(ok), C.c_int64(n), C.c_int64(p), C.c_int(kind), _p(outs[0][0]), _p(outs[0][1])), outs)
+
+
+def bbands(x, p=20, up=2.0, dn=2.0, ok=None):
+    return _call("pqo_bbands", [_col(x, ok)], [p], 3, floats=[up, dn])
+
+
+def macd(x, fast=12, slow=26, signal=9, ok=None):
+    return _call("pqo_macd", [_col(x, ok)], [fast, slow, signal], 3)
+
+
+def midprice(h, l, p=14, hok=None, lok=None):
+    return _call("pqo_midprice", [_col(h, hok), _col(l, lok)], [p], 1)
+
+
+def trange(h, l, c, hok=None, lok=None, cok=None):
+    return _call("pqo_trange", [_col(h, hok), _col(l, lok), _col(c, cok)], [], 1)
+
+
+def atr(h, l, c, p=14, hok=None, lok=None, cok=None):
+    return _call("pqo_atr", [_col(h, hok), _col(l, lok), _col(c, cok)], [p], 1)
+
+
+def natr(h, l, c, p=14, hok=None, lok=None, cok=None):
+    return _call("pqo_natr", [_col(h, hok), _col(l, lok), _col(c, cok)], [p], 1)
+
+
+def willr(h, l, c, p=14, hok=None, lok=None, cok=None):
+    return _call("pqo_willr", [_col(h, hok), _col(l, lok), _col(c, cok)], [p], 1)
+
+
+def cci(h, l, c, p=14, hok=None, lok=None, cok=None):
+    return _call("pqo_cci", [_col(h, hok), _col(l, lok), _col(c, cok)], [p], 1)
+
+
+def obv(c, v, cok=None, vok=None):
+    return _call("pqo_obv", [_col(c, cok), _col(v, vok)], [], 1)
+
+
+def ad(h, l, c, v, hok=None, lok=None, cok=None, vok=None):
+    return _call("pqo_ad", [_col(h, hok), _col(l, lok), _col(c, cok), _col(v, vok)], [], 1)
+
+
+def adosc(h, l, c, v, fast=3, slow=10, hok=None, lok=None, cok=None, vok=None):
+    return _call("pqo_adosc", [_col(h, hok), _col(l, lok), _col(c, cok), _col(v, vok)], [fast, slow], 1)
+
+
+def mfi(h, l, c, v, p=14):
+    return _call("pqo_mfi", [_col(h), _col(l), _col(c), _col(v)], [p], 1)
+
+
+def stoch(h, l, c, fastk=5, slowk=3, slowk_matype=0, slowd=3, slowd_matype=0, hok=None, lok=None, cok=None):
+    return _call("pqo_stoch", [_col(h, hok), _col(l, lok), _col(c, cok)],
+                 [fastk, slowk, slowk_matype, slowd, slowd_matype], 2)
+
+
+def stochf(h, l, c, fastk=5, fastd=3, fastd_matype=0, hok=None, lok=None, cok=None):
+    return _call("pqo_stochf", [_col(h, hok), _col(l, lok), _col(c, cok)], [fastk, fastd, fastd_matype], 2)
+
+
+def kdj(h, l, c, fastk=9, k=3, d=3):
+    return _call("pqo_kdj", [_col(h), _col(l), _col(c)], [fastk, k, d], 3)
+
+
+def donchian(h, l, p=20):
+    h, _ = _col(h)
+    l, _ = _col(l)
+    n = len(h)
+    outs = _outs(n, 2)
+    f = lib().pqo_donchian
+    f.restype = C.c_int
+    rc = f(_p(h), _p(l), C.c_int64(n), C.c_int64(p), _p(outs[0][0]), _p(outs[0][1]), _p(outs[1][0]), _p(outs[1][1]))
+    return _ret(rc, outs)
+
+
+N_OUT = 21
+OUTPUT_NAMES = ["sma", "ema", "tema", "trima", "bb_upper", "bb_middle", "bb_lower", "macd",
+                "macd_signal", "macd_hist", "rsi", "trange", "atr", "natr", "obv", "ad",
+                "kdj_k", "kdj_d", "kdj_j", "willr", "midprice"]
+
+
+def suite_panel(c, h, l, v, params: SuiteParams | None = None, threads: int = 0):
+    """c/h/l/v: float64 [n_symbols, pitch] C-contiguous (n_bars = pitch).  Returns
+    (out [21, n_symbols, n_bars] float64, ok [21, n_symbols, n_bars] bool, threads_used)."""
+    params = params or SuiteParams.default()
+    c, h, l, v = (np.ascontiguousarray(a, dtype=np.float64) for a in (c, h, l, v))
+    S, N = c.shape
+    out = np.empty((N_OUT, S, N), np.float64)
+    ok = np.empty((N_OUT, S, N), np.uint8)
+    f = lib().pqo_suite_panel
+    f.restype = C.c_int
+    rc = f(_p(c), _p(h), _p(l), _p(v), C.c_int64(S), C.c_int64(N), C.c_int64(N), C.byref(params),
+           _p(out), _p(ok), C.c_int(threads))
+    if rc < 0:
+        raise OracleError(rc)
+    return out, ok.astype(bool), rc
