@@ -1,0 +1,6 @@
+"""polars_quant_b200 -- B200-native drop-in for polars-quant's src/talib indicator engine on
+wide `{symbol}_{column}` f64 panels.  CUDA (sm_100a) behind a C ABI; no CPU fallback."""
+from . import _native
+from .panel import Engine, Panel, get_engine
+
+__all__ = ["Engine", "Panel", "get_engine", "_native"]

@@ -1,0 +1,121 @@
+"""ctypes binding of libpqb200.so (include/pqb200.h).  There is no fallback: if the shared
+library is missing, or no B200 is present when a compute entry point is called, this raises."""
+from __future__ import annotations
+
+import ctypes as C
+import subprocess
+from pathlib import Path
+
+_PKG = Path(__file__).resolve().parent
+LIB_PATH = _PKG / "libpqb200.so"
+
+N_FIELDS = 4
+N_OUTPUTS = 21
+CLOSE, HIGH, LOW, VOLUME = 0, 1, 2, 3
+OUTPUT_NAMES = ["sma", "ema", "tema", "trima", "bb_upper", "bb_middle", "bb_lower", "macd",
+                "macd_signal", "macd_hist", "rsi", "trange", "atr", "natr", "obv", "ad",
+                "kdj_k", "kdj_d", "kdj_j", "willr", "midprice"]
+IND = {"sma": 1 << 0, "ema": 1 << 1, "tema": 1 << 2, "trima": 1 << 3, "bbands": 1 << 4, "macd": 1 << 5,
+       "rsi": 1 << 6, "trange": 1 << 7, "atr": 1 << 8, "natr": 1 << 9, "obv": 1 << 10, "ad": 1 << 11,
+       "kdj": 1 << 12, "willr": 1 << 13, "midprice": 1 << 14}
+IND_ALL = (1 << 15) - 1
+
+ERR_NAMES = {-1: "PQB_ERR_NO_DEVICE", -2: "PQB_ERR_CUDA", -3: "PQB_ERR_INVALID", -4: "PQB_ERR_UNSUPPORTED",
+             -5: "PQB_ERR_NULLS", -6: "PQB_ERR_ALLOC"}
+
+
+class PqbError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__("%s: %s" % (ERR_NAMES.get(code, code), msg))
+        self.code = code
+
+
+class SuiteParams(C.Structure):
+    _fields_ = [("indicators", C.c_uint32), ("sma_period", C.c_int32), ("ema_period", C.c_int32),
+                ("tema_period", C.c_int32), ("trima_period", C.c_int32), ("bbands_period", C.c_int32),
+                ("bbands_nbdevup", C.c_double), ("bbands_nbdevdn", C.c_double), ("macd_fast", C.c_int32),
+                ("macd_slow", C.c_int32), ("macd_signal", C.c_int32), ("rsi_period", C.c_int32),
+                ("atr_period", C.c_int32), ("natr_period", C.c_int32), ("kdj_fastk", C.c_int32),
+                ("kdj_slowk", C.c_int32), ("kdj_slowd", C.c_int32), ("willr_period", C.c_int32),
+                ("midprice_period", C.c_int32)]
+
+
+class Col(C.Structure):
+    _fields_ = [("values", C.c_void_p), ("validity", C.c_void_p), ("offset", C.c_int64), ("len", C.c_int64)]
+
+
+class OutCol(C.Structure):
+    _fields_ = [("values", C.c_void_p), ("validity", C.c_void_p)]
+
+
+def build(force: bool = False) -> Path:
+    """Compiles libpqb200.so in-tree with nvcc for sm_100a (works without a GPU)."""
+    srcs = list((_PKG / "csrc").glob("*.cu*")) + list((_PKG.parent / "include").glob("*.h"))
+    if force or not LIB_PATH.exists() or any(s.stat().st_mtime > LIB_PATH.stat().st_mtime for s in srcs):
+        r = subprocess.run(["make", "-C", str(_PKG / "csrc"), "-B"], capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("building libpqb200.so failed:\n" + r.stdout + r.stderr)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.exists():
+            raise RuntimeError("libpqb200.so is not built (run python -c 'import __graft_entry__ as g; g.build()'); "
+                               "there is no CPU fallback")
+        L = C.CDLL(str(LIB_PATH))
+        L.pqb_last_error.restype = C.c_char_p
+        L.pqb_panel_pitch.restype = C.c_int64
+        L.pqb_panel_pitch.argtypes = [C.c_void_p]
+        L.pqb_panel_validity_pitch.restype = C.c_int64
+        L.pqb_panel_validity_pitch.argtypes = [C.c_void_p]
+        for name in ("pqb_panel_host_field", "pqb_panel_host_output", "pqb_panel_host_validity",
+                     "pqb_panel_device_field", "pqb_panel_device_output", "pqb_panel_device_validity"):
+            f = getattr(L, name)
+            f.restype = C.c_void_p
+            f.argtypes = [C.c_void_p, C.c_int]
+        L.pqb_engine_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+        L.pqb_engine_destroy.argtypes = [C.c_void_p]
+        L.pqb_engine_destroy.restype = None
+        L.pqb_panel_create.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_uint32, C.c_uint32, C.c_int,
+                                       C.POINTER(C.c_void_p)]
+        L.pqb_panel_destroy.argtypes = [C.c_void_p]
+        L.pqb_panel_destroy.restype = None
+        L.pqb_panel_set_column.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64]
+        L.pqb_panel_set_starts.argtypes = [C.c_void_p, C.c_void_p]
+        L.pqb_panel_upload.argtypes = [C.c_void_p]
+        L.pqb_panel_download.argtypes = [C.c_void_p]
+        L.pqb_panel_sync.argtypes = [C.c_void_p]
+        L.pqb_suite_run.argtypes = [C.c_void_p, C.POINTER(SuiteParams)]
+        L.pqb_suite_run_host.argtypes = [C.c_void_p, C.POINTER(SuiteParams), C.c_int64]
+        L.pqb_panel_get_output.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_int64]
+        L.pqb_panel_fill_synthetic.argtypes = [C.c_void_p, C.c_uint64, C.c_double, C.c_int]
+        L.pqb_suite_time.argtypes = [C.c_void_p, C.POINTER(SuiteParams), C.c_int, C.c_int, C.POINTER(C.c_float),
+                                     C.POINTER(C.c_float), C.POINTER(C.c_int)]
+        L.pqb_suite_time_host.argtypes = [C.c_void_p, C.POINTER(SuiteParams), C.c_int64, C.c_int, C.c_int,
+                                          C.POINTER(C.c_float)]
+        L.pqb_flush_l2.argtypes = [C.c_void_p]
+        L.pqb_suite_params_default.argtypes = [C.POINTER(SuiteParams)]
+        L.pqb_suite_params_default.restype = None
+        _lib = L
+    return _lib
+
+
+def check(rc: int):
+    if rc != 0:
+        raise PqbError(rc, lib().pqb_last_error().decode("utf-8", "replace"))
+
+
+def default_params(indicators: int = IND_ALL, **overrides) -> SuiteParams:
+    p = SuiteParams()
+    lib().pqb_suite_params_default(C.byref(p))
+    p.indicators = indicators
+    for k, v in overrides.items():
+        if not hasattr(p, k):
+            raise TypeError("unknown suite parameter %r" % k)
+        setattr(p, k, v)
+    return p

@@ -1,0 +1,170 @@
+"""Panel-level host API: the new layer between the reference's Python shims (L4) and its
+per-column kernels (L1) -- SURVEY.md section 1.  A Panel packs the `{symbol}_{field}` f64
+columns of a wide DataFrame into the GPU layout [field][symbol][pitch], runs the fused
+indicator suite in one launch and hands the 21 output columns back with Arrow validity."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _native as N
+
+
+class Engine:
+    """One per GPU (pqb_engine)."""
+
+    def __init__(self, device: int = 0):
+        self._h = C.c_void_p()
+        N.check(N.lib().pqb_engine_create(device, C.byref(self._h)))
+        self.device = device
+
+    def close(self):
+        if self._h:
+            N.lib().pqb_engine_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def flush_l2(self):
+        N.check(N.lib().pqb_flush_l2(self._h))
+
+
+_engines: dict[int, Engine] = {}
+
+
+def get_engine(device: int = 0) -> Engine:
+    if device not in _engines:
+        _engines[device] = Engine(device)
+    return _engines[device]
+
+
+class Panel:
+    FIELDS = {"close": N.CLOSE, "high": N.HIGH, "low": N.LOW, "volume": N.VOLUME}
+
+    def __init__(self, n_symbols: int, n_bars: int, engine: Engine | None = None, fields_mask: int = 0xF,
+                 outputs_mask: int = (1 << N.N_OUTPUTS) - 1, host_staging: bool = True):
+        self.engine = engine or get_engine(0)
+        self.n_symbols, self.n_bars = int(n_symbols), int(n_bars)
+        self.outputs_mask = outputs_mask
+        self.host_staging = host_staging
+        self._h = C.c_void_p()
+        N.check(N.lib().pqb_panel_create(self.engine._h, n_symbols, n_bars, fields_mask, outputs_mask,
+                                         1 if host_staging else 0, C.byref(self._h)))
+        self.pitch = N.lib().pqb_panel_pitch(self._h)
+        self.validity_pitch = N.lib().pqb_panel_validity_pitch(self._h)
+
+    def close(self):
+        if self._h:
+            N.lib().pqb_panel_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- host staging views (zero-copy numpy over pinned memory) ----
+    def host_field(self, field) -> np.ndarray:
+        f = self.FIELDS[field] if isinstance(field, str) else field
+        ptr = N.lib().pqb_panel_host_field(self._h, f)
+        if not ptr:
+            raise ValueError("panel has no host staging for field %r" % (field,))
+        buf = (C.c_double * (self.n_symbols * self.pitch)).from_address(ptr)
+        return np.frombuffer(buf, dtype=np.float64).reshape(self.n_symbols, self.pitch)
+
+    def host_output(self, k: int) -> np.ndarray:
+        ptr = N.lib().pqb_panel_host_output(self._h, k)
+        if not ptr:
+            raise ValueError("output %d not allocated" % k)
+        buf = (C.c_double * (self.n_symbols * self.pitch)).from_address(ptr)
+        return np.frombuffer(buf, dtype=np.float64).reshape(self.n_symbols, self.pitch)[:, :self.n_bars]
+
+    def host_validity(self, k: int) -> np.ndarray:
+        """bool [n_symbols, n_bars] unpacked from the Arrow LSB-first bitmaps."""
+        ptr = N.lib().pqb_panel_host_validity(self._h, k)
+        if not ptr:
+            raise ValueError("output %d not allocated" % k)
+        buf = (C.c_uint8 * (self.n_symbols * self.validity_pitch)).from_address(ptr)
+        bits = np.frombuffer(buf, dtype=np.uint8).reshape(self.n_symbols, self.validity_pitch)
+        return np.unpackbits(bits, axis=1, bitorder="little")[:, :self.n_bars].astype(bool)
+
+    # ---- loading ----
+    def set_fields(self, close=None, high=None, low=None, volume=None, starts=None):
+        """Each argument: float64 [n_symbols, n_bars].  Written straight into pinned staging."""
+        for name, a in (("close", close), ("high", high), ("low", low), ("volume", volume)):
+            if a is None:
+                continue
+            a = np.asarray(a, dtype=np.float64)
+            if a.shape != (self.n_symbols, self.n_bars):
+                raise ValueError("%s has shape %r, panel is %r" % (name, a.shape, (self.n_symbols, self.n_bars)))
+            v = self.host_field(name)
+            v[:, :self.n_bars] = a
+            v[:, self.n_bars:] = 0.0
+        if starts is not None:
+            s = np.ascontiguousarray(starts, dtype=np.int32)
+            N.check(N.lib().pqb_panel_set_starts(self._h, s.ctypes.data_as(C.c_void_p)))
+
+    def set_column(self, symbol: int, field, values: np.ndarray, validity: np.ndarray | None = None, offset: int = 0):
+        """One Arrow column: values float64, validity = packed LSB-first bitmap (uint8) or None."""
+        f = self.FIELDS[field] if isinstance(field, str) else field
+        values = np.ascontiguousarray(values, dtype=np.float64)
+        vp = None if validity is None else np.ascontiguousarray(validity, dtype=np.uint8).ctypes.data_as(C.c_void_p)
+        N.check(N.lib().pqb_panel_set_column(self._h, symbol, f, values.ctypes.data_as(C.c_void_p), vp, offset,
+                                             len(values) - offset))
+
+    def fill_synthetic(self, seed: int = 0xC0FFEE, sigma: float = 0.02, to_host: bool = False):
+        N.check(N.lib().pqb_panel_fill_synthetic(self._h, seed, sigma, 1 if to_host else 0))
+
+    # ---- running ----
+    def upload(self):
+        N.check(N.lib().pqb_panel_upload(self._h))
+
+    def download(self):
+        N.check(N.lib().pqb_panel_download(self._h))
+
+    def sync(self):
+        N.check(N.lib().pqb_panel_sync(self._h))
+
+    def run(self, params: N.SuiteParams | None = None):
+        """Device-resident fused suite (async)."""
+        params = params or N.default_params()
+        N.check(N.lib().pqb_suite_run(self._h, C.byref(params)))
+
+    def run_host(self, params: N.SuiteParams | None = None, chunk_symbols: int = 0):
+        """End-to-end: pinned staging -> device -> suite -> pinned staging (pipelined)."""
+        params = params or N.default_params()
+        N.check(N.lib().pqb_suite_run_host(self._h, C.byref(params), chunk_symbols))
+
+    def compute(self, params: N.SuiteParams | None = None):
+        """upload + run + download + sync; returns {name: (values, validity)}."""
+        self.upload()
+        self.run(params)
+        self.download()
+        self.sync()
+        return self.outputs()
+
+    def outputs(self):
+        res = {}
+        for k, name in enumerate(N.OUTPUT_NAMES):
+            if self.outputs_mask >> k & 1:
+                res[name] = (self.host_output(k), self.host_validity(k))
+        return res
+
+    # ---- measurement ----
+    def time_device(self, params=None, warmup: int = 3, iters: int = 20):
+        params = params or N.default_params()
+        tot, fused, nl = C.c_float(), C.c_float(), C.c_int()
+        N.check(N.lib().pqb_suite_time(self._h, C.byref(params), warmup, iters, C.byref(tot), C.byref(fused), C.byref(nl)))
+        return tot.value, fused.value, nl.value
+
+    def time_host(self, params=None, chunk_symbols: int = 0, warmup: int = 1, iters: int = 3):
+        params = params or N.default_params()
+        tot = C.c_float()
+        N.check(N.lib().pqb_suite_time_host(self._h, C.byref(params), chunk_symbols, warmup, iters, C.byref(tot)))
+        return tot.value
