@@ -3,11 +3,12 @@ library is missing, or no B200 is present when a compute entry point is called, 
 from __future__ import annotations
 
 import ctypes as C
+import os
 import subprocess
 from pathlib import Path
 
 _PKG = Path(__file__).resolve().parent
-LIB_PATH = _PKG / "libpqb200.so"
+LIB_PATH = Path(os.environ["PQB_LIB"]) if os.environ.get("PQB_LIB") else _PKG / "libpqb200.so"
 
 N_FIELDS = 4
 N_OUTPUTS = 21

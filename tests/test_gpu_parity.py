@@ -11,7 +11,7 @@ from oracle import pqo
 
 pytestmark = pytest.mark.gpu
 
-REL, ABS = 1e-10, 1e-12
+import tolerances as T
 
 
 @pytest.fixture(scope="module")
@@ -20,23 +20,10 @@ def pq():
     return m
 
 
-def _check_output(name, gv, gok, ov, ook):
-    assert np.array_equal(gok, ook), f"{name}: validity differs at {np.argwhere(gok != ook)[:5].tolist()}"
-    assert np.isnan(gv[~gok]).all(), f"{name}: null slots must hold NaN"
-    a, b = gv[ook], ov[ook]
-    if name == "obv":
-        assert np.array_equal(a, b), "obv must be bit-exact"
-        return 0.0
-    if name == "ad":
-        scale = np.maximum.accumulate(np.abs(np.nan_to_num(ov)), axis=-1)[ook]
-        err = np.abs(a - b)
-        assert (err <= ABS + REL * scale).all(), f"ad: max err {err.max()} (scaled tol)"
-        return float((err / np.maximum(scale, 1e-300)).max())
-    err = np.abs(a - b)
-    tol = ABS + REL * np.abs(b)
-    bad = err > tol
-    assert not bad.any(), f"{name}: {bad.sum()} of {bad.size} outside tol; worst err {err[bad].max()} at value {b[bad][np.argmax(err[bad])]}"
-    return float((err / np.maximum(np.abs(b), 1e-300)).max()) if err.size else 0.0
+def _assert_parity(res, out, ok, close, nbdevup=2.0, nbdevdn=2.0, skip=()):
+    fails, worst = T.compare_all(res, out, ok, close, pqo.OUTPUT_NAMES, nbdevup, nbdevdn, skip)
+    assert not fails, "\n".join(fails)
+    return worst
 
 
 def _run_vs_oracle(pq, d, params=None, oparams=None, starts=None):
@@ -55,10 +42,9 @@ def _run_vs_oracle(pq, d, params=None, oparams=None, starts=None):
                 continue
             o, k, _ = pqo.suite_panel(*(d[f][s:s + 1, a:] for f in ("close", "high", "low", "volume")), oparams)
             out[:, s, a:], ok[:, s, a:] = o[:, 0], k[:, 0]
-    worst = {}
-    for j, name in enumerate(pqo.OUTPUT_NAMES):
-        gv, gok = res[name]
-        worst[name] = _check_output(name, gv, gok, out[j], ok[j])
+    up = oparams.bb_up if oparams is not None else 2.0
+    dn = oparams.bb_dn if oparams is not None else 2.0
+    worst = _assert_parity(res, out, ok, d["close"], up, dn)
     panel.close()
     return worst
 
@@ -66,7 +52,7 @@ def _run_vs_oracle(pq, d, params=None, oparams=None, starts=None):
 def test_suite_small_panel(pq):
     d = synth.ohlcv(67, 700, seed=42)            # 5.5 tiles, ragged tail, more symbols than one CTA
     worst = _run_vs_oracle(pq, d)
-    print("max rel err per output:", {k: f"{v:.2e}" for k, v in worst.items()})
+    print("worst err/tol per output:", {k: f"{v:.2e}" for k, v in worst.items()})
 
 
 def test_suite_single_symbol_config1(pq):
@@ -88,22 +74,29 @@ def test_suite_leading_nulls(pq):
     _run_vs_oracle(pq, d, starts=starts)
 
 
-@pytest.mark.parametrize("seed", range(4))
+@pytest.mark.parametrize("seed", range(8))
 def test_suite_random_periods(pq, seed):
+    """Random periods.  bbands_period >= 2: with period 1 the reference's sum_sq/p - mean^2 is pure
+    rounding drift of its running sums (true variance 0) that sqrt() amplifies to ~1e-6 -- no
+    reordered evaluation can reproduce that noise (DESIGN.md 'numerics').  Odd seeds tie
+    ema==tema and natr==atr so the steady tile path (stage sharing) runs with non-default periods."""
     from polars_quant_b200 import _native as N
     rng = np.random.default_rng(seed)
     r = lambda lo, hi: int(rng.integers(lo, hi + 1))
     kw = dict(sma_period=r(1, 32), ema_period=r(1, 60), tema_period=r(1, 40), trima_period=r(1, 60),
-              bbands_period=r(1, 32), bbands_nbdevup=1.5, bbands_nbdevdn=2.5, macd_fast=r(1, 20),
+              bbands_period=r(2, 32), bbands_nbdevup=1.5, bbands_nbdevdn=2.5, macd_fast=r(1, 20),
               macd_slow=r(2, 40), macd_signal=r(1, 15), rsi_period=r(1, 30), atr_period=r(1, 30),
               natr_period=r(1, 30), kdj_fastk=r(1, 32), kdj_slowk=r(1, 8), kdj_slowd=r(1, 8),
               willr_period=r(1, 32), midprice_period=r(1, 32))
+    if seed % 2 == 1:
+        kw["ema_period"] = kw["tema_period"]
+        kw["natr_period"] = kw["atr_period"]
     params = N.default_params(**kw)
     op = pqo.SuiteParams(kw["sma_period"], kw["ema_period"], kw["tema_period"], kw["trima_period"],
                          kw["bbands_period"], 1.5, 2.5, kw["macd_fast"], kw["macd_slow"], kw["macd_signal"],
                          kw["rsi_period"], kw["atr_period"], kw["natr_period"], kw["kdj_fastk"],
                          kw["kdj_slowk"], kw["kdj_slowd"], kw["willr_period"], kw["midprice_period"])
-    d = synth.ohlcv(33, 515, seed=900 + seed)
+    d = synth.ohlcv(33, 900, seed=900 + seed)
     _run_vs_oracle(pq, d, params, op)
 
 
@@ -120,16 +113,19 @@ def test_suite_flat_and_tied_values(pq):
     panel.set_fields(d["close"], d["high"], d["low"], d["volume"])
     res = panel.compute()
     out, ok, _ = pqo.suite_panel(d["close"], d["high"], d["low"], d["volume"])
-    for j, name in enumerate(pqo.OUTPUT_NAMES):
-        if name in ("kdj_k", "kdj_d", "kdj_j"):
-            # flat 9-bar windows give 0/0 = NaN in fastk; the reference's running sum then stays NaN
-            # forever (sum -= NaN), the tile-local prefix recovers: compare up to the first NaN only.
-            first_nan = np.argmax(np.isnan(out[j]) & ok[j], axis=1)
-            for s in range(S):
-                lim = first_nan[s] if np.isnan(out[j, s]).any() else N
-                _check_output(name, res[name][0][s, :lim], res[name][1][s, :lim], out[j, s, :lim], ok[j, s, :lim])
-            continue
-        _check_output(name, res[name][0], res[name][1], out[j], ok[j])
+    # flat 9-bar windows give 0/0 = NaN in fastk; the reference's running sum then stays NaN forever
+    # (sum -= NaN), the tile-local prefix sum recovers once the NaN leaves the window: K/D/J are
+    # compared up to the first NaN only (DESIGN.md "NaN inputs").
+    _assert_parity(res, out, ok, d["close"], skip=("kdj_k", "kdj_d", "kdj_j"))
+    ctx = {"close": d["close"], "out": {n: out[j] for j, n in enumerate(pqo.OUTPUT_NAMES)}}
+    for name in ("kdj_k", "kdj_d", "kdj_j"):
+        j = pqo.OUTPUT_NAMES.index(name)
+        for s in range(S):
+            nanpos = np.flatnonzero(np.isnan(out[j, s]) & ok[j, s])
+            lim = int(nanpos[0]) if nanpos.size else N
+            c1 = {"close": d["close"][s, :lim], "out": {n: v[s, :lim] for n, v in ctx["out"].items()}}
+            nbad, _, msg = T.compare(name, res[name][0][s, :lim], res[name][1][s, :lim], out[j, s, :lim], ok[j, s, :lim], c1)
+            assert nbad == 0, msg
     panel.close()
 
 
@@ -144,10 +140,8 @@ def test_config2_full_size_against_oracle(pq):
     res = panel.outputs()
     d = {f: np.ascontiguousarray(panel.host_field(f)[:, :N]) for f in ("close", "high", "low", "volume")}
     out, ok, _ = pqo.suite_panel(d["close"], d["high"], d["low"], d["volume"])
-    worst = {}
-    for j, name in enumerate(pqo.OUTPUT_NAMES):
-        worst[name] = _check_output(name, res[name][0], res[name][1], out[j], ok[j])
-    print("config2 max rel err per output:", {k: f"{v:.2e}" for k, v in worst.items()})
+    worst = _assert_parity(res, out, ok, d["close"])
+    print("config2 worst err/tol per output:", {k: f"{v:.2e}" for k, v in worst.items()})
     panel.close()
 
 
