@@ -131,15 +131,22 @@ PQB_API int pqb_device_count(void);
 PQB_API int pqb_engine_create(int device, pqb_engine **out);
 PQB_API void pqb_engine_destroy(pqb_engine *e);
 
-/* ---- panel: GPU layout [field][symbol][pitch] f64, pitch = n_bars rounded up to 16 ------ */
-/* Allocates device planes for the fields in `fields_mask` (bit f = enum pqb_field f), the
+/* ---- panel ----------------------------------------------------------------------------
+ * Host side (pinned staging, everything that crosses this ABI): row-major [symbol][pitch] f64,
+ * pitch = n_bars rounded up to 16, plus Arrow LSB-first validity bitmaps per output column.
+ * Device side: every plane is TILED [symbol block of 32][bar group of 4][32 symbols][4 bars]:
+ * element (s, t) lives at ((s/32 * groups + t/4) * 32 + s%32) * 4 + t%4 doubles, `groups` from
+ * pqb_panel_tiled_shape().  Upload / download / pqb_suite_run_host convert on the device.
+ * Allocates device planes for the fields in `fields_mask` (bit f = enum pqb_field f), the
  * output planes for `outputs_mask` (bit k = enum pqb_output k), output validity bitmaps and
- * (if `host_staging` != 0) pinned host staging of the same shapes for the transfer path. */
+ * (if `host_staging` != 0) pinned host staging plus the device transfer buffers. */
 PQB_API int pqb_panel_create(pqb_engine *e, int64_t n_symbols, int64_t n_bars, uint32_t fields_mask,
                      uint32_t outputs_mask, int host_staging, pqb_panel **out);
 PQB_API void pqb_panel_destroy(pqb_panel *p);
 PQB_API int64_t pqb_panel_pitch(const pqb_panel *p);          /* doubles per symbol row */
 PQB_API int64_t pqb_panel_validity_pitch(const pqb_panel *p); /* bytes per symbol row of a bitmap */
+/* Geometry of the tiled device planes: symbol blocks and (padded) bar groups per block. */
+PQB_API int pqb_panel_tiled_shape(const pqb_panel *p, int64_t *n_blocks, int64_t *groups);
 
 /* Copies one Arrow column (values + optional validity bitmap + bit/element offset, as in the
  * Arrow C Data Interface the reference's plugin boundary receives) into the
@@ -175,7 +182,8 @@ PQB_API int pqb_suite_run_host(pqb_panel *p, const pqb_suite_params *params, int
 PQB_API int pqb_panel_get_output(pqb_panel *p, int64_t symbol, int output, double *values,
                          uint8_t *validity, int64_t len);
 
-/* Device pointers for callers that stay on the GPU (cuDF-style hosts, the bench). */
+/* Device pointers (TILED planes; validity bitmaps are row-major [symbol][validity_pitch]) for
+ * callers that stay on the GPU. */
 PQB_API const double *pqb_panel_device_field(const pqb_panel *p, int field);
 PQB_API const double *pqb_panel_device_output(const pqb_panel *p, int output);
 PQB_API const uint8_t *pqb_panel_device_validity(const pqb_panel *p, int output);

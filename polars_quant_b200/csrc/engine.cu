@@ -1,6 +1,12 @@
 // engine.cu -- host side of libpqb200.so: the C ABI of include/pqb200.h over the fused
 // sm_100a suite kernel (suite_kernel.cuh).  Plain CUDA runtime; no torch, no CPU fallback:
 // every compute entry point fails loudly when there is no device.
+//
+// Device layout: every plane (4 inputs, 21 outputs) is "tiled"
+//   [symbol block of 32][bar group of 4][32 symbols][4 bars]       (suite_kernel.cuh)
+// Host staging (pinned) and everything that crosses the ABI is row-major Arrow-style
+// [symbol][pitch] f64 + LSB-first validity bitmaps; pack_kernel / unpack_kernel convert on the
+// device, chunk by chunk, on the way in and out.
 #include "../../include/pqb200.h"
 #include "suite_kernel.cuh"
 
@@ -66,6 +72,9 @@ extern "C" void pqb_suite_params_default(pqb_suite_params *p) {
 // ---------------------------------------------------------------------------------------
 // engine / panel objects
 // ---------------------------------------------------------------------------------------
+static constexpr int kMaxSmem = 227 * 1024;      // opt-in dynamic shared memory per CTA on sm_100
+static constexpr int kFixedSmem = NS * STAGE_DOUBLES * 8 + 2 * NS * 8;   // TMA stages + mbarriers
+
 struct pqb_engine {
     int device = 0;
     int sm_count = 0;
@@ -73,7 +82,6 @@ struct pqb_engine {
     cudaStream_t h2d = nullptr, d2h = nullptr;
     void *flush_buf = nullptr;
     size_t flush_bytes = 0;
-    int ctas_per_sm32 = 0, ctas_per_sm128 = 0;
     std::mutex mu;                       // guards the single-column scratch panel
     pqb_panel *scratch = nullptr;
     int64_t scratch_bars = 0;
@@ -82,36 +90,31 @@ struct pqb_engine {
 struct pqb_panel {
     pqb_engine *e = nullptr;
     int64_t n_symbols = 0, n_bars = 0, pitch = 0, words_per_row = 0;
+    int64_t n_blocks = 0, groups = 0;    // tiled geometry
+    size_t plane_doubles = 0;            // n_blocks * groups * 128
     uint32_t fields_mask = 0, outputs_mask = 0;
-    double *d_in[PQB_N_FIELDS] = {};
-    double *d_out[PQB_N_OUTPUTS] = {};
-    uint32_t *d_bits[PQB_N_OUTPUTS] = {};
+    double *d_in[PQB_N_FIELDS] = {};     // tiled
+    double *d_out[PQB_N_OUTPUTS] = {};   // tiled
+    uint32_t *d_bits[PQB_N_OUTPUTS] = {};// row-major bitmaps
     int *d_start = nullptr;
     bool starts_nonzero = false;
-    // pinned staging
+    // pinned row-major staging
     double *h_in[PQB_N_FIELDS] = {};
     double *h_out[PQB_N_OUTPUTS] = {};
     uint32_t *h_bits[PQB_N_OUTPUTS] = {};
     std::vector<int32_t> h_start;
     bool staging = false;
-    cudaEvent_t ev[4] = {};
+    // device row-major transfer buffers: 2 x chunk for inputs and outputs (double-buffered)
+    int64_t chunk_symbols = 0;
+    double *d_xin[2] = {};               // [n_fields_alloc][chunk][pitch]
+    double *d_xout[2] = {};              // [n_outputs_alloc][chunk][pitch]
+    int n_in_alloc = 0, n_out_alloc = 0;
+    int in_slot[PQB_N_FIELDS] = {}, out_slot[PQB_N_OUTPUTS] = {};
+    cudaEvent_t ev_packed[2] = {}, ev_d2h[2] = {};
 };
 
 static int set_dev(const pqb_engine *e) {
     CU(cudaSetDevice(e->device));
-    return PQB_OK;
-}
-
-static constexpr int kWarpsPerCta = PQB_CTA_THREADS / 32;
-
-template <int HALO>
-static int configure_kernel(int *ctas_per_sm) {
-    const int smem = kWarpsPerCta * WarpSmem<HALO>::BYTES;
-    CU(cudaFuncSetAttribute(suite_fused_kernel<HALO>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    CU(cudaFuncSetAttribute(suite_fused_kernel<HALO>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    int n = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, suite_fused_kernel<HALO>, PQB_CTA_THREADS, smem));
-    *ctas_per_sm = std::max(n, 1);
     return PQB_OK;
 }
 
@@ -138,10 +141,8 @@ extern "C" int pqb_engine_create(int device, pqb_engine **out) {
     CU(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&e->h2d, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&e->d2h, cudaStreamNonBlocking));
-    int rc = configure_kernel<32>(&e->ctas_per_sm32);
-    if (rc) { delete e; return rc; }
-    rc = configure_kernel<128>(&e->ctas_per_sm128);
-    if (rc) { delete e; return rc; }
+    CU(cudaFuncSetAttribute(suite_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+    CU(cudaFuncSetAttribute(suite_fused_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     *out = e;
     return PQB_OK;
 }
@@ -173,42 +174,61 @@ extern "C" int pqb_panel_create(pqb_engine *e, int64_t n_symbols, int64_t n_bars
     p->n_bars = n_bars;
     p->pitch = (n_bars + 15) / 16 * 16;
     p->words_per_row = (n_bars + 31) / 32;
+    p->n_blocks = (n_symbols + SYM - 1) / SYM;
+    p->groups = ((n_bars + GB - 1) / GB + SG - 1) / SG * SG;
+    p->plane_doubles = (size_t)p->n_blocks * p->groups * GROUP_DOUBLES;
     p->fields_mask = fields_mask;
     p->outputs_mask = outputs_mask;
     p->staging = host_staging != 0;
-    const size_t plane = (size_t)n_symbols * p->pitch * sizeof(double);
+    const size_t hplane = (size_t)n_symbols * p->pitch * sizeof(double);
+    const size_t dplane = p->plane_doubles * sizeof(double);
     const size_t bplane = (size_t)n_symbols * p->words_per_row * sizeof(uint32_t);
     auto bail = [&](cudaError_t ce, const char *what) {
-        fail(ce == cudaErrorMemoryAllocation ? PQB_ERR_ALLOC : PQB_ERR_CUDA, "pqb_panel_create: %s: %s", what,
-             cudaGetErrorString(ce));
+        const int code = ce == cudaErrorMemoryAllocation ? PQB_ERR_ALLOC : PQB_ERR_CUDA;
+        fail(code, "pqb_panel_create: %s: %s", what, cudaGetErrorString(ce));
+        cudaGetLastError();
         pqb_panel_destroy(p);
-        return g_err.empty() ? PQB_ERR_CUDA : (ce == cudaErrorMemoryAllocation ? PQB_ERR_ALLOC : PQB_ERR_CUDA);
+        return code;
     };
     cudaError_t ce;
     for (int f = 0; f < PQB_N_FIELDS; ++f) {
         if (!(fields_mask >> f & 1)) continue;
-        // + one tile of slack: the last TMA tile of the last row never reads past the allocation
-        if ((ce = cudaMalloc(&p->d_in[f], plane + TILE * sizeof(double))) != cudaSuccess) return bail(ce, "cudaMalloc(field)");
-        if ((ce = cudaMemsetAsync(p->d_in[f], 0, plane + TILE * sizeof(double), e->stream)) != cudaSuccess) return bail(ce, "memset");
+        if ((ce = cudaMalloc(&p->d_in[f], dplane)) != cudaSuccess) return bail(ce, "cudaMalloc(field)");
+        if ((ce = cudaMemsetAsync(p->d_in[f], 0, dplane, e->stream)) != cudaSuccess) return bail(ce, "memset");
+        p->in_slot[f] = p->n_in_alloc++;
         if (p->staging) {
-            if ((ce = cudaMallocHost(&p->h_in[f], plane)) != cudaSuccess) return bail(ce, "cudaMallocHost(field)");
-            memset(p->h_in[f], 0, plane);
+            if ((ce = cudaMallocHost(&p->h_in[f], hplane)) != cudaSuccess) return bail(ce, "cudaMallocHost(field)");
+            memset(p->h_in[f], 0, hplane);
         }
     }
     for (int k = 0; k < PQB_N_OUTPUTS; ++k) {
         if (!(outputs_mask >> k & 1)) continue;
-        if ((ce = cudaMalloc(&p->d_out[k], plane)) != cudaSuccess) return bail(ce, "cudaMalloc(output)");
+        if ((ce = cudaMalloc(&p->d_out[k], dplane)) != cudaSuccess) return bail(ce, "cudaMalloc(output)");
         if ((ce = cudaMalloc(&p->d_bits[k], bplane)) != cudaSuccess) return bail(ce, "cudaMalloc(validity)");
+        p->out_slot[k] = p->n_out_alloc++;
         if (p->staging) {
-            if ((ce = cudaMallocHost(&p->h_out[k], plane)) != cudaSuccess) return bail(ce, "cudaMallocHost(output)");
+            if ((ce = cudaMallocHost(&p->h_out[k], hplane)) != cudaSuccess) return bail(ce, "cudaMallocHost(output)");
             if ((ce = cudaMallocHost(&p->h_bits[k], bplane)) != cudaSuccess) return bail(ce, "cudaMallocHost(validity)");
         }
     }
-    if ((ce = cudaMalloc(&p->d_start, (size_t)n_symbols * sizeof(int))) != cudaSuccess) return bail(ce, "cudaMalloc(start)");
-    if ((ce = cudaMemsetAsync(p->d_start, 0, (size_t)n_symbols * sizeof(int), e->stream)) != cudaSuccess) return bail(ce, "memset");
+    if (p->staging) {
+        // transfer chunk: whole symbol blocks, at most ~32 MB per plane
+        int64_t cs = (32ll << 20) / (p->pitch * (int64_t)sizeof(double));
+        cs = std::max<int64_t>(SYM, cs / SYM * SYM);
+        cs = std::min<int64_t>(cs, p->n_blocks * SYM);
+        p->chunk_symbols = cs;
+        const size_t cplane = (size_t)cs * p->pitch * sizeof(double);
+        for (int b = 0; b < 2; ++b) {
+            if ((ce = cudaMalloc(&p->d_xin[b], cplane * p->n_in_alloc)) != cudaSuccess) return bail(ce, "cudaMalloc(xfer in)");
+            if (p->n_out_alloc &&
+                (ce = cudaMalloc(&p->d_xout[b], cplane * p->n_out_alloc)) != cudaSuccess) return bail(ce, "cudaMalloc(xfer out)");
+            if ((ce = cudaEventCreateWithFlags(&p->ev_packed[b], cudaEventDisableTiming)) != cudaSuccess) return bail(ce, "event");
+            if ((ce = cudaEventCreateWithFlags(&p->ev_d2h[b], cudaEventDisableTiming)) != cudaSuccess) return bail(ce, "event");
+        }
+    }
+    if ((ce = cudaMalloc(&p->d_start, (size_t)p->n_blocks * SYM * sizeof(int))) != cudaSuccess) return bail(ce, "cudaMalloc(start)");
+    if ((ce = cudaMemsetAsync(p->d_start, 0, (size_t)p->n_blocks * SYM * sizeof(int), e->stream)) != cudaSuccess) return bail(ce, "memset");
     p->h_start.assign((size_t)n_symbols, 0);
-    for (auto &ev : p->ev)
-        if ((ce = cudaEventCreate(&ev)) != cudaSuccess) return bail(ce, "cudaEventCreate");
     if ((ce = cudaStreamSynchronize(e->stream)) != cudaSuccess) return bail(ce, "sync");
     *out = p;
     return PQB_OK;
@@ -220,16 +240,25 @@ extern "C" void pqb_panel_destroy(pqb_panel *p) {
     for (auto &q : p->d_in) if (q) cudaFree(q);
     for (auto &q : p->d_out) if (q) cudaFree(q);
     for (auto &q : p->d_bits) if (q) cudaFree(q);
+    for (auto &q : p->d_xin) if (q) cudaFree(q);
+    for (auto &q : p->d_xout) if (q) cudaFree(q);
     if (p->d_start) cudaFree(p->d_start);
     for (auto &q : p->h_in) if (q) cudaFreeHost(q);
     for (auto &q : p->h_out) if (q) cudaFreeHost(q);
     for (auto &q : p->h_bits) if (q) cudaFreeHost(q);
-    for (auto &ev : p->ev) if (ev) cudaEventDestroy(ev);
+    for (auto &ev : p->ev_packed) if (ev) cudaEventDestroy(ev);
+    for (auto &ev : p->ev_d2h) if (ev) cudaEventDestroy(ev);
     delete p;
 }
 
 extern "C" int64_t pqb_panel_pitch(const pqb_panel *p) { return p ? p->pitch : 0; }
 extern "C" int64_t pqb_panel_validity_pitch(const pqb_panel *p) { return p ? p->words_per_row * 4 : 0; }
+extern "C" int pqb_panel_tiled_shape(const pqb_panel *p, int64_t *n_blocks, int64_t *groups) {
+    if (!p) return fail(PQB_ERR_INVALID, "pqb_panel_tiled_shape: NULL");
+    if (n_blocks) *n_blocks = p->n_blocks;
+    if (groups) *groups = p->groups;
+    return PQB_OK;
+}
 extern "C" double *pqb_panel_host_field(pqb_panel *p, int f) {
     return (p && f >= 0 && f < PQB_N_FIELDS) ? p->h_in[f] : nullptr;
 }
@@ -282,7 +311,7 @@ extern "C" int pqb_panel_set_starts(pqb_panel *p, const int32_t *starts) {
     p->starts_nonzero = false;
     for (int64_t s = 0; s < p->n_symbols; ++s) {
         if (starts[s] < 0) return fail(PQB_ERR_INVALID, "pqb_panel_set_starts: negative start");
-        p->h_start[(size_t)s] = std::min<int64_t>(starts[s], p->n_bars);
+        p->h_start[(size_t)s] = (int32_t)std::min<int64_t>(starts[s], p->n_bars);
         if (starts[s]) p->starts_nonzero = true;
     }
     int rc = set_dev(p->e);
@@ -293,15 +322,80 @@ extern "C" int pqb_panel_set_starts(pqb_panel *p, const int32_t *starts) {
     return PQB_OK;
 }
 
+// ---- layout conversion launches (chunk = symbols [s0, s0+ns), s0 a multiple of 32) ----
+static int launch_conv(pqb_panel *p, bool pack, const double *const *rowmajor, double *const *tiled, int n_planes,
+                       int64_t s0, int64_t ns, cudaStream_t st) {
+    if (n_planes == 0 || ns == 0) return PQB_OK;
+    ConvArgs V{};
+    V.n_planes = n_planes;
+    for (int i = 0; i < n_planes; ++i) {
+        if (pack) { V.src[i] = rowmajor[i]; V.dst[i] = tiled[i]; }
+        else { V.src[i] = tiled[i]; V.dst[i] = const_cast<double *>(rowmajor[i]); }
+    }
+    V.n_symbols = (int)ns;
+    V.n_bars = (int)p->n_bars;
+    V.pitch = (int)p->pitch;
+    V.groups = (int)p->groups;
+    V.block0 = (int)(s0 / SYM);
+    dim3 grid((unsigned)((p->groups + 7) / 8), (unsigned)((ns + SYM - 1) / SYM));
+    if (pack) pack_kernel<<<grid, 256, 0, st>>>(V);
+    else unpack_kernel<<<grid, 256, 0, st>>>(V);
+    CU(cudaGetLastError());
+    return PQB_OK;
+}
+
 extern "C" int pqb_panel_upload(pqb_panel *p) {
     if (!p || !p->staging) return fail(PQB_ERR_INVALID, "pqb_panel_upload: no host staging");
     int rc = set_dev(p->e);
     if (rc) return rc;
-    const size_t plane = (size_t)p->n_symbols * p->pitch * sizeof(double);
-    for (int f = 0; f < PQB_N_FIELDS; ++f)
-        if (p->d_in[f]) CU(cudaMemcpyAsync(p->d_in[f], p->h_in[f], plane, cudaMemcpyHostToDevice, p->e->stream));
-    CU(cudaMemcpyAsync(p->d_start, p->h_start.data(), (size_t)p->n_symbols * sizeof(int), cudaMemcpyHostToDevice,
-                       p->e->stream));
+    cudaStream_t st = p->e->stream;
+    const size_t cplane = (size_t)p->chunk_symbols * p->pitch;
+    for (int64_t s0 = 0; s0 < p->n_symbols; s0 += p->chunk_symbols) {
+        const int64_t ns = std::min(p->chunk_symbols, p->n_symbols - s0);
+        const double *rm[PQB_N_FIELDS];
+        double *tl[PQB_N_FIELDS];
+        int n = 0;
+        for (int f = 0; f < PQB_N_FIELDS; ++f) {
+            if (!p->d_in[f]) continue;
+            double *buf = p->d_xin[0] + cplane * p->in_slot[f];
+            CU(cudaMemcpyAsync(buf, p->h_in[f] + (size_t)s0 * p->pitch, (size_t)ns * p->pitch * sizeof(double),
+                               cudaMemcpyHostToDevice, st));
+            rm[n] = buf; tl[n] = p->d_in[f]; ++n;
+        }
+        if ((rc = launch_conv(p, true, rm, tl, n, s0, ns, st))) return rc;
+    }
+    CU(cudaMemcpyAsync(p->d_start, p->h_start.data(), (size_t)p->n_symbols * sizeof(int), cudaMemcpyHostToDevice, st));
+    return PQB_OK;
+}
+
+// tiled device planes -> pinned row-major staging (outputs + validity, or the input fields)
+static int download_planes(pqb_panel *p, bool inputs) {
+    cudaStream_t st = p->e->stream;
+    const size_t cplane = (size_t)p->chunk_symbols * p->pitch;
+    for (int64_t s0 = 0; s0 < p->n_symbols; s0 += p->chunk_symbols) {
+        const int64_t ns = std::min(p->chunk_symbols, p->n_symbols - s0);
+        const double *rm[PQB_N_OUTPUTS];
+        double *tl[PQB_N_OUTPUTS];
+        double *host[PQB_N_OUTPUTS];
+        int n = 0;
+        if (inputs) {
+            for (int f = 0; f < PQB_N_FIELDS; ++f)
+                if (p->d_in[f]) { rm[n] = p->d_xin[0] + cplane * p->in_slot[f]; tl[n] = p->d_in[f]; host[n] = p->h_in[f]; ++n; }
+        } else {
+            for (int k = 0; k < PQB_N_OUTPUTS; ++k)
+                if (p->d_out[k]) { rm[n] = p->d_xout[0] + cplane * p->out_slot[k]; tl[n] = p->d_out[k]; host[n] = p->h_out[k]; ++n; }
+        }
+        int rc = launch_conv(p, false, rm, tl, n, s0, ns, st);
+        if (rc) return rc;
+        for (int i = 0; i < n; ++i)
+            CU(cudaMemcpyAsync(host[i] + (size_t)s0 * p->pitch, rm[i], (size_t)ns * p->pitch * sizeof(double),
+                               cudaMemcpyDeviceToHost, st));
+    }
+    if (!inputs) {
+        const size_t bplane = (size_t)p->n_symbols * p->words_per_row * sizeof(uint32_t);
+        for (int k = 0; k < PQB_N_OUTPUTS; ++k)
+            if (p->d_out[k]) CU(cudaMemcpyAsync(p->h_bits[k], p->d_bits[k], bplane, cudaMemcpyDeviceToHost, st));
+    }
     return PQB_OK;
 }
 
@@ -309,14 +403,7 @@ extern "C" int pqb_panel_download(pqb_panel *p) {
     if (!p || !p->staging) return fail(PQB_ERR_INVALID, "pqb_panel_download: no host staging");
     int rc = set_dev(p->e);
     if (rc) return rc;
-    const size_t plane = (size_t)p->n_symbols * p->pitch * sizeof(double);
-    const size_t bplane = (size_t)p->n_symbols * p->words_per_row * sizeof(uint32_t);
-    for (int k = 0; k < PQB_N_OUTPUTS; ++k) {
-        if (!p->d_out[k]) continue;
-        CU(cudaMemcpyAsync(p->h_out[k], p->d_out[k], plane, cudaMemcpyDeviceToHost, p->e->stream));
-        CU(cudaMemcpyAsync(p->h_bits[k], p->d_bits[k], bplane, cudaMemcpyDeviceToHost, p->e->stream));
-    }
-    return PQB_OK;
+    return download_planes(p, false);
 }
 
 extern "C" int pqb_panel_sync(pqb_panel *p) {
@@ -345,28 +432,16 @@ extern "C" int pqb_panel_get_output(pqb_panel *p, int64_t symbol, int output, do
 // ---------------------------------------------------------------------------------------
 // parameters -> kernel arguments
 // ---------------------------------------------------------------------------------------
-static EmaK make_ema_k(int p, double alpha) {
-    EmaK k{};
-    k.alpha = alpha;
-    k.p = p;
-    k.pd = (double)p;
-    const double a = 1.0 - alpha;
-    double pw = a;
-    for (int i = 0; i < 4; ++i) { k.pw[i] = pw; pw *= a; }
-    double A = k.pw[3];
-    for (int j = 0; j < 5; ++j) { k.A[j] = A; A *= A; }
-    return k;
-}
 static inline double ema_alpha(int p) { return 2.0 / ((double)p + 1.0); }   // overlap.rs:669
 
 struct Built {
     SuiteArgs a;
-    int halo;          // 32 or 128
+    int lead[PQB_N_OUTPUTS];   // first valid index of each output relative to the symbol start
 };
 
 static int build_args(const pqb_panel *p, const pqb_suite_params *sp, Built *out) {
     SuiteArgs &A = out->a;
-    memset(&A, 0, sizeof A);
+    memset(out, 0, sizeof *out);
     const int n_bars = (int)p->n_bars;
     const int NEVER = n_bars;                       // lead that makes a column all-null
     uint32_t ind = sp->indicators & PQB_IND_ALL;
@@ -384,49 +459,48 @@ static int build_args(const pqb_panel *p, const pqb_suite_params *sp, Built *out
     if ((ind & PQB_IND_OBV) && (rc = need_fields(C | V, "obv"))) return rc;
     if ((ind & PQB_IND_AD) && (rc = need_fields(C | H | L | V, "ad"))) return rc;
 
-    for (int f = 0; f < PQB_N_FIELDS; ++f) A.in[f] = p->d_in[f] ? p->d_in[f] : nullptr;
-    // the TMA producer always copies all four planes of a tile: alias missing ones to a present one
-    const double *any = nullptr;
-    for (int f = 0; f < PQB_N_FIELDS; ++f) if (A.in[f]) { any = A.in[f]; break; }
-    for (int f = 0; f < PQB_N_FIELDS; ++f) if (!A.in[f]) A.in[f] = any;
-    for (int k = 0; k < PQB_N_OUTPUTS; ++k) { A.out[k] = nullptr; A.lead[k] = NEVER; }
+    for (int f = 0; f < PQB_N_FIELDS; ++f) A.in[f] = p->d_in[f];
+    for (int k = 0; k < PQB_N_OUTPUTS; ++k) { A.out[k] = nullptr; out->lead[k] = NEVER; }
     A.start = p->starts_nonzero ? p->d_start : nullptr;
     A.n_symbols = (int)p->n_symbols;
     A.n_bars = n_bars;
-    A.pitch = (int)p->pitch;
+    A.n_blocks = (int)p->n_blocks;
+    A.groups = (int)p->groups;
+    A.block0 = 0;
 
-    int max_sum_window = 1, max_ext_window = 1;
+    int steady = 1;
     auto neg = [&](int v, const char *name) -> int {
         return v < 0 ? fail(PQB_ERR_INVALID, "%s period %d is negative", name, v) : PQB_OK;
     };
     auto want = [&](int k) { return p->d_out[k] != nullptr; };
     auto bind = [&](int k, long long lead) {
-        if (want(k)) { A.out[k] = p->d_out[k]; A.lead[k] = (int)std::min<long long>(lead, NEVER); }
+        if (want(k)) { A.out[k] = p->d_out[k]; out->lead[k] = (int)std::min<long long>(lead, NEVER); }
     };
     // A period of 0 makes the reference return an all-null column (guards overlap.rs:663,874,...):
-    // the output is bound with lead = NEVER and its group stays off.
-    auto null_only = [&](int k) { if (want(k)) { A.out[k] = p->d_out[k]; A.lead[k] = NEVER; } };
-    // (all-null columns are NaN-filled by run_suite: no group stores them)
+    // the output is bound with lead = NEVER and its group stays off (run_suite NaN-fills it).
+    auto null_only = [&](int k) { if (want(k)) { A.out[k] = p->d_out[k]; out->lead[k] = NEVER; } };
+    auto upto = [&](long long j) { steady = (int)std::min<long long>(std::max<long long>(steady, j), 1ll << 30); };
 
     if (ind & PQB_IND_SMA) {
         if ((rc = neg(sp->sma_period, "sma"))) return rc;
         if (sp->sma_period == 0) { null_only(PQB_OUT_SMA); }
-        else { A.groups |= G_SMA; A.sma_p = sp->sma_period; A.inv_sma = 1.0 / (double)sp->sma_period;
-               bind(PQB_OUT_SMA, sp->sma_period - 1); max_sum_window = std::max(max_sum_window, sp->sma_period); }
+        else { A.gmask |= G_SMA; A.sma_p = sp->sma_period; A.inv_sma = 1.0 / (double)sp->sma_period;
+               bind(PQB_OUT_SMA, sp->sma_period - 1); upto(sp->sma_period); }
     }
     if (ind & PQB_IND_TEMA) {
         if ((rc = neg(sp->tema_period, "tema"))) return rc;
         const int tp = sp->tema_period;
         // guard overlap.rs:1180: n < 3p-2 -> all null (equivalent to lead >= n)
         if (tp == 0) { null_only(PQB_OUT_TEMA); }
-        else { A.groups |= G_TEMA; A.k_tema = make_ema_k(tp, ema_alpha(tp)); bind(PQB_OUT_TEMA, 3ll * tp - 3); }
+        // tp == 1: the reference's `count == p` branch wins over `count == 3p-2` -> first value at index 1
+        else { A.gmask |= G_TEMA; A.tema_p = tp; A.a_tema = ema_alpha(tp);
+               bind(PQB_OUT_TEMA, tp == 1 ? 1 : 3ll * tp - 3); upto(tp == 1 ? 2 : 3ll * tp - 2); }
     }
     if (ind & PQB_IND_EMA) {
         if ((rc = neg(sp->ema_period, "ema"))) return rc;
         const int ep = sp->ema_period;
         if (ep == 0) { null_only(PQB_OUT_EMA); }
-        else { A.groups |= G_EMA; A.k_ema = make_ema_k(ep, ema_alpha(ep)); bind(PQB_OUT_EMA, ep - 1);
-               A.ema_shares_tema = (A.groups & G_TEMA) && sp->tema_period == ep; }
+        else { A.gmask |= G_EMA; A.ema_p = ep; A.a_ema = ema_alpha(ep); bind(PQB_OUT_EMA, ep - 1); upto(ep); }
     }
     if (ind & PQB_IND_TRIMA) {
         if ((rc = neg(sp->trima_period, "trima"))) return rc;
@@ -434,49 +508,50 @@ static int build_args(const pqb_panel *p, const pqb_suite_params *sp, Built *out
         int n1, n2;
         if (tp % 2 == 1) { n1 = tp / 2 + 1; n2 = n1; } else { n1 = tp / 2; n2 = n1 + 1; }   // overlap.rs:1314-1323
         if (n1 == 0) { null_only(PQB_OUT_TRIMA); }
-        else { A.groups |= G_TRIMA; A.tri_n1 = n1; A.tri_n2 = n2; A.inv_tri1 = 1.0 / (double)n1; A.inv_tri2 = 1.0 / (double)n2;
-               bind(PQB_OUT_TRIMA, (long long)n1 + n2 - 2); max_sum_window = std::max(max_sum_window, std::max(n1, n2)); }
+        else { A.gmask |= G_TRIMA; A.tri_n1 = n1; A.tri_n2 = n2; A.inv_tri1 = 1.0 / (double)n1; A.inv_tri2 = 1.0 / (double)n2;
+               bind(PQB_OUT_TRIMA, (long long)n1 + n2 - 2); upto((long long)n1 + n2 - 1); }
     }
     if (ind & PQB_IND_BBANDS) {
         if ((rc = neg(sp->bbands_period, "bbands"))) return rc;
         const int bp = sp->bbands_period;
         if (bp == 0) { for (int k = 4; k <= 6; ++k) { null_only(k); } }
-        else { A.groups |= G_BB; A.bb_p = bp; A.bb_pd = (double)bp; A.inv_bb = 1.0 / (double)bp;
+        else { A.gmask |= G_BB; A.bb_p = bp; A.bb_pd = (double)bp;
                A.bb_up = sp->bbands_nbdevup; A.bb_dn = sp->bbands_nbdevdn;
                for (int k = 4; k <= 6; ++k) bind(k, bp - 1);
-               max_sum_window = std::max(max_sum_window, bp); }
+               upto(bp); }
     }
     if (ind & PQB_IND_MACD) {
         const int f = sp->macd_fast, s = sp->macd_slow, g = sp->macd_signal;
         if ((rc = neg(f, "macd fast")) || (rc = neg(s, "macd slow")) || (rc = neg(g, "macd signal"))) return rc;
         if (f == 0 || s == 0 || g == 0)
             return fail(PQB_ERR_UNSUPPORTED, "macd with a zero period (reference yields partial nulls) is not built");
-        A.groups |= G_MACD;
-        A.k_macd_f = make_ema_k(f, ema_alpha(f)); A.k_macd_s = make_ema_k(s, ema_alpha(s)); A.k_macd_g = make_ema_k(g, ema_alpha(g));
-        A.macd_dif_lead = std::max(f, s) - 1;
-        bind(PQB_OUT_MACD, A.macd_dif_lead); bind(PQB_OUT_MACD_SIGNAL, g - 1);
-        bind(PQB_OUT_MACD_HIST, std::max(A.macd_dif_lead, g - 1));
+        A.gmask |= G_MACD;
+        A.macd_f = f; A.macd_s = s; A.macd_g = g;
+        A.a_mf = ema_alpha(f); A.a_ms = ema_alpha(s); A.a_mg = ema_alpha(g);
+        const int dl = std::max(f, s) - 1;
+        bind(PQB_OUT_MACD, dl); bind(PQB_OUT_MACD_SIGNAL, g - 1);
+        bind(PQB_OUT_MACD_HIST, std::max(dl, g - 1));
+        upto(std::max(std::max(f, s), g));
     }
     if (ind & PQB_IND_RSI) {
         if ((rc = neg(sp->rsi_period, "rsi"))) return rc;
         const int rp = sp->rsi_period;
         if (rp == 0) { null_only(PQB_OUT_RSI); }
-        else { A.groups |= G_RSI; A.k_rsi = make_ema_k(rp, 1.0 / (double)rp); bind(PQB_OUT_RSI, rp - 1); }   // D1
+        else { A.gmask |= G_RSI; A.rsi_p = rp; A.a_rsi = 1.0 / (double)rp; bind(PQB_OUT_RSI, rp - 1); upto(rp); }   // D1
     }
-    if (ind & PQB_IND_TRANGE) { A.groups |= G_TRANGE; bind(PQB_OUT_TRANGE, 1); }
+    if (ind & PQB_IND_TRANGE) { A.gmask |= G_TRANGE; bind(PQB_OUT_TRANGE, 1); }
     if (ind & PQB_IND_ATR) {
         if (sp->atr_period <= 0) return fail(PQB_ERR_INVALID, "atr period %d: 2p-1 underflows in the reference", sp->atr_period);
         const int ep = 2 * sp->atr_period - 1;                                               // volatility.rs:30
-        A.groups |= G_ATR; A.k_atr = make_ema_k(ep, ema_alpha(ep)); bind(PQB_OUT_ATR, (long long)ep);
+        A.gmask |= G_ATR; A.atr_ep = ep; A.a_atr = ema_alpha(ep); bind(PQB_OUT_ATR, (long long)ep); upto((long long)ep + 1);
     }
     if (ind & PQB_IND_NATR) {
         if (sp->natr_period <= 0) return fail(PQB_ERR_INVALID, "natr period %d: 2p-1 underflows in the reference", sp->natr_period);
         const int ep = 2 * sp->natr_period - 1;
-        A.groups |= G_NATR; A.k_natr = make_ema_k(ep, ema_alpha(ep)); bind(PQB_OUT_NATR, (long long)ep);
-        A.natr_shares_atr = (A.groups & G_ATR) && sp->atr_period == sp->natr_period;
+        A.gmask |= G_NATR; A.natr_ep = ep; A.a_natr = ema_alpha(ep); bind(PQB_OUT_NATR, (long long)ep); upto((long long)ep + 1);
     }
-    if (ind & PQB_IND_OBV) { A.groups |= G_OBV; bind(PQB_OUT_OBV, 1); }
-    if (ind & PQB_IND_AD) { A.groups |= G_AD; bind(PQB_OUT_AD, 0); }
+    if (ind & PQB_IND_OBV) { A.gmask |= G_OBV; bind(PQB_OUT_OBV, 1); }
+    if (ind & PQB_IND_AD) { A.gmask |= G_AD; bind(PQB_OUT_AD, 0); }
     if (ind & PQB_IND_KDJ) {
         const int k = sp->kdj_fastk, sk = sp->kdj_slowk, sd = sp->kdj_slowd;
         if ((rc = neg(k, "kdj fastk")) || (rc = neg(sk, "kdj slowk")) || (rc = neg(sd, "kdj slowd"))) return rc;
@@ -485,39 +560,55 @@ static int build_args(const pqb_panel *p, const pqb_suite_params *sp, Built *out
             if (k != 0 && sk != 0 && sd == 0)
                 return fail(PQB_ERR_UNSUPPORTED, "kdj with slowd_period 0 (K valid, D null) is not built");
         } else {
-            A.groups |= G_KDJ; A.kdj_k = k; A.kdj_sk = sk; A.kdj_sd = sd; A.inv_sk = 1.0 / (double)sk; A.inv_sd = 1.0 / (double)sd;
+            A.gmask |= G_KDJ; A.kdj_k = k; A.kdj_sk = sk; A.kdj_sd = sd; A.inv_sk = 1.0 / (double)sk; A.inv_sd = 1.0 / (double)sd;
             bind(PQB_OUT_KDJ_K, (long long)k + sk - 2); bind(PQB_OUT_KDJ_D, (long long)k + sk + sd - 3);
             bind(PQB_OUT_KDJ_J, (long long)k + sk + sd - 3);
-            max_ext_window = std::max(max_ext_window, k); max_sum_window = std::max(max_sum_window, std::max(sk, sd));
+            upto((long long)k + sk + sd - 2);
         }
     }
     if (ind & PQB_IND_WILLR) {
         if ((rc = neg(sp->willr_period, "willr"))) return rc;
         if (sp->willr_period == 0) { null_only(PQB_OUT_WILLR); }
-        else { A.groups |= G_WILLR; A.willr_p = sp->willr_period; bind(PQB_OUT_WILLR, sp->willr_period - 1);
-               max_ext_window = std::max(max_ext_window, sp->willr_period); }
+        else { A.gmask |= G_WILLR; A.willr_p = sp->willr_period; bind(PQB_OUT_WILLR, sp->willr_period - 1); upto(sp->willr_period); }
     }
     if (ind & PQB_IND_MIDPRICE) {
         if (sp->midprice_period <= 0)
             return fail(PQB_ERR_UNSUPPORTED, "midprice period %d (reference: never-expiring deque) is not built", sp->midprice_period);
-        A.groups |= G_MIDPRICE; A.mid_p = sp->midprice_period; bind(PQB_OUT_MIDPRICE, 0);
-        max_ext_window = std::max(max_ext_window, sp->midprice_period);
+        A.gmask |= G_MIDPRICE; A.mid_p = sp->midprice_period; bind(PQB_OUT_MIDPRICE, 0);
     }
-    {
-        bool all_bound = true;
-        int L = 0;
-        for (int k = 0; k < PQB_N_OUTPUTS; ++k) { all_bound &= A.out[k] != nullptr; L = std::max(L, A.lead[k]); }
-        A.steady_ok = (A.groups == G_ALL) && all_bound && A.ema_shares_tema && A.natr_shares_atr;
-        if (A.steady_ok && A.sma_p == 30 && A.tri_n1 == 15 && A.tri_n2 == 16 && A.bb_p == 20 && A.kdj_k == 9 &&
-            A.kdj_sk == 3 && A.kdj_sd == 3 && A.willr_p == 14 && A.mid_p == 14)
-            A.steady_ok = 2;        // window periods == the reference's Python defaults: baked-in path
-        A.steady_lead = L + 1;
-    }
-    if (max_ext_window > 32)
-        return fail(PQB_ERR_UNSUPPORTED, "rolling max/min window %d > 32 is not built yet", max_ext_window);
-    if (max_sum_window > 128)
-        return fail(PQB_ERR_UNSUPPORTED, "windowed-sum period %d > 128 is not built yet", max_sum_window);
-    out->halo = (max_sum_window > 32) ? 128 : 32;
+    A.steady_lead = steady;
+
+    // roles with work, planes to stage
+    A.roles = 0; A.n_roles = 0; A.fields = 0;
+    for (int r = 0; r < N_ROLES; ++r)
+        if (A.gmask & ROLE_GROUPS[r]) { A.roles |= 1u << r; ++A.n_roles; }
+    if (A.gmask & (G_SMA | G_EMA | G_TEMA | G_TRIMA | G_BB | G_MACD | G_RSI | G_TRANGE | G_ATR | G_NATR | G_OBV | G_AD | G_KDJ | G_WILLR)) A.fields |= F_C;
+    if (A.gmask & (G_TRANGE | G_ATR | G_NATR | G_AD | G_KDJ | G_WILLR | G_MIDPRICE)) A.fields |= F_H | F_L;
+    if (A.gmask & (G_OBV | G_AD)) A.fields |= F_V;
+
+    // shared-memory rings (slots of 32 doubles)
+    long long off = 0;
+    auto take = [&](int slots) { const long long o = off; off += (long long)std::max(slots, 1) * SYM; return (int)std::min<long long>(o, 1ll << 30); };
+    int cmax = 0;
+    if (A.gmask & G_SMA) cmax = std::max(cmax, A.sma_p);
+    if (A.gmask & G_BB) cmax = std::max(cmax, A.bb_p);
+    if (A.gmask & G_TRIMA) cmax = std::max(cmax, A.tri_n1);
+    A.cring_slots = cmax + 1; A.off_cring = take(A.cring_slots);
+    A.tring_slots = ((A.gmask & G_TRIMA) ? A.tri_n2 : 0) + 1; A.off_tring = take(A.tring_slots);
+    A.fk_slots = ((A.gmask & G_KDJ) ? A.kdj_sk : 0) + 1; A.off_fk = take(A.fk_slots);
+    A.sk_slots = ((A.gmask & G_KDJ) ? A.kdj_sd : 0) + 1; A.off_sk = take(A.sk_slots);
+    const int wp = (A.gmask & G_WILLR) ? A.willr_p : 0;
+    const int mp = ((A.gmask & G_MIDPRICE) && !((A.gmask & G_WILLR) && A.willr_p == A.mid_p)) ? A.mid_p : 0;
+    const int kp = (A.gmask & G_KDJ) ? A.kdj_k : 0;
+    A.off_wh = take(wp); A.off_wl = take(wp);
+    A.off_mh = take(mp); A.off_ml = take(mp);
+    A.off_kh = take(kp); A.off_kl = take(kp);
+    const long long smem = (long long)kFixedSmem + off * 8;
+    if (smem > kMaxSmem)
+        return fail(PQB_ERR_UNSUPPORTED,
+                    "windows too long for one launch: the per-block rings need %lld bytes of shared memory (limit %d); "
+                    "run long-window indicators in separate calls", smem, kMaxSmem);
+    A.smem_bytes = (int)smem;
     return PQB_OK;
 }
 
@@ -525,44 +616,6 @@ static int build_args(const pqb_panel *p, const pqb_suite_params *sp, Built *out
 __global__ void nan_fill_kernel(double *p, size_t n) {
     const double nn = __longlong_as_double(0x7ff8000000000000LL);
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = nn;
-}
-
-static int launch_suite(pqb_engine *e, const Built &b, uint32_t *const *bits, int words_per_row,
-                        cudaEvent_t ev_after_fused, int *launches) {
-    int n_launch = 0;
-    if (b.a.groups) {
-        const int per_sm = (b.halo == 32) ? e->ctas_per_sm32 : e->ctas_per_sm128;
-        const long long warps_needed = b.a.n_symbols;
-        int grid = e->sm_count * per_sm;
-        grid = (int)std::min<long long>(grid, (warps_needed + kWarpsPerCta - 1) / kWarpsPerCta);
-        if (b.halo == 32)
-            suite_fused_kernel<32><<<grid, PQB_CTA_THREADS, kWarpsPerCta * WarpSmem<32>::BYTES, e->stream>>>(b.a);
-        else
-            suite_fused_kernel<128><<<grid, PQB_CTA_THREADS, kWarpsPerCta * WarpSmem<128>::BYTES, e->stream>>>(b.a);
-        CU(cudaGetLastError());
-        ++n_launch;
-    }
-    if (ev_after_fused) CU(cudaEventRecord(ev_after_fused, e->stream));
-    ValidityArgs V{};
-    bool any = false;
-    for (int k = 0; k < PQB_N_OUTPUTS; ++k) {
-        V.bits[k] = b.a.out[k] ? bits[k] : nullptr;
-        V.lead[k] = b.a.lead[k];
-        any |= V.bits[k] != nullptr;
-    }
-    V.start = b.a.start;
-    V.n_symbols = b.a.n_symbols;
-    V.n_bars = b.a.n_bars;
-    V.words_per_row = words_per_row;
-    if (any) {
-        const long long total = (long long)V.n_symbols * V.words_per_row;
-        const int grid = (int)std::min<long long>((total + 255) / 256, (long long)e->sm_count * 8);
-        validity_kernel<<<grid, 256, 0, e->stream>>>(V);
-        CU(cudaGetLastError());
-        ++n_launch;
-    }
-    if (launches) *launches = n_launch;
-    return PQB_OK;
 }
 
 // which outputs does an enabled group actually store?  (used for the period-0 NaN fill)
@@ -586,32 +639,68 @@ static uint32_t outputs_of_groups(unsigned g) {
     return m;
 }
 
+// Launches the suite over symbol blocks [b0, b0+nb) (+ NaN fills + validity bitmaps of those symbols).
+static int launch_suite(pqb_panel *p, const Built &full, int64_t b0, int64_t nb, cudaEvent_t ev_after_fused,
+                        int *launches) {
+    pqb_engine *e = p->e;
+    int n_launch = 0;
+    const uint32_t stored = outputs_of_groups(full.a.gmask);
+    const size_t boff = (size_t)b0 * p->groups * GROUP_DOUBLES, bn = (size_t)nb * p->groups * GROUP_DOUBLES;
+    for (int k = 0; k < PQB_N_OUTPUTS; ++k) {
+        if (full.a.out[k] && !(stored >> k & 1)) {
+            nan_fill_kernel<<<e->sm_count * 4, 256, 0, e->stream>>>(full.a.out[k] + boff, bn);
+            CU(cudaGetLastError());
+            ++n_launch;
+        }
+    }
+    if (full.a.gmask) {
+        SuiteArgs a = full.a;
+        a.block0 = (int)b0;
+        suite_fused_kernel<<<(unsigned)nb, CTA_THREADS, a.smem_bytes, e->stream>>>(a);
+        CU(cudaGetLastError());
+        ++n_launch;
+    }
+    if (ev_after_fused) CU(cudaEventRecord(ev_after_fused, e->stream));
+    const int64_t s0 = b0 * SYM, ns = std::min<int64_t>(nb * SYM, p->n_symbols - s0);
+    ValidityArgs V{};
+    bool any = false;
+    for (int k = 0; k < PQB_N_OUTPUTS; ++k) {
+        V.bits[k] = (full.a.out[k] && p->d_bits[k]) ? p->d_bits[k] + (size_t)s0 * p->words_per_row : nullptr;
+        V.lead[k] = full.lead[k];
+        any |= V.bits[k] != nullptr;
+    }
+    V.start = full.a.start ? full.a.start + s0 : nullptr;
+    V.n_symbols = (int)ns;
+    V.n_bars = full.a.n_bars;
+    V.words_per_row = (int)p->words_per_row;
+    if (any) {
+        const long long total = (long long)V.n_symbols * V.words_per_row;
+        const int grid = (int)std::min<long long>((total + 255) / 256, (long long)e->sm_count * 8);
+        validity_kernel<<<grid, 256, 0, e->stream>>>(V);
+        CU(cudaGetLastError());
+        ++n_launch;
+    }
+    if (launches) *launches = n_launch;
+    return PQB_OK;
+}
+
 static int run_suite(pqb_panel *p, const pqb_suite_params *sp, cudaEvent_t ev_after_fused, int *launches) {
     if (!p || !sp) return fail(PQB_ERR_INVALID, "pqb_suite_run: NULL argument");
     int rc = set_dev(p->e);
     if (rc) return rc;
     Built b;
     if ((rc = build_args(p, sp, &b))) return rc;
-    int extra = 0;
-    const uint32_t stored = outputs_of_groups(b.a.groups);
-    for (int k = 0; k < PQB_N_OUTPUTS; ++k) {
-        if (b.a.out[k] && !(stored >> k & 1)) {
-            const size_t n = (size_t)p->n_symbols * p->pitch;
-            nan_fill_kernel<<<p->e->sm_count * 4, 256, 0, p->e->stream>>>(b.a.out[k], n);
-            CU(cudaGetLastError());
-            ++extra;
-        }
-    }
-    int nl = 0;
-    rc = launch_suite(p->e, b, p->d_bits, (int)p->words_per_row, ev_after_fused, &nl);
-    if (launches) *launches = nl + extra;
-    return rc;
+    return launch_suite(p, b, 0, p->n_blocks, ev_after_fused, launches);
 }
 
 extern "C" int pqb_suite_run(pqb_panel *p, const pqb_suite_params *sp) { return run_suite(p, sp, nullptr, nullptr); }
 
 // ---------------------------------------------------------------------------------------
-// end-to-end host path: chunked upload -> suite -> download over pinned staging
+// end-to-end host path: per chunk of symbol blocks
+//   h2d stream : pinned row-major fields -> device row-major buffer [c % 2]
+//   compute    : pack -> fused suite -> validity -> unpack into device row-major buffer [c % 2]
+//   d2h stream : outputs + bitmaps -> pinned staging
+// so both DMA directions overlap the kernels of neighbouring chunks.
 // ---------------------------------------------------------------------------------------
 extern "C" int pqb_suite_run_host(pqb_panel *p, const pqb_suite_params *sp, int64_t chunk_symbols) {
     if (!p || !sp) return fail(PQB_ERR_INVALID, "pqb_suite_run_host: NULL argument");
@@ -621,43 +710,55 @@ extern "C" int pqb_suite_run_host(pqb_panel *p, const pqb_suite_params *sp, int6
     pqb_engine *e = p->e;
     Built full;
     if ((rc = build_args(p, sp, &full))) return rc;
-    if (chunk_symbols <= 0) chunk_symbols = std::max<int64_t>(1, (int64_t)e->sm_count * 8);
+    if (chunk_symbols <= 0 || chunk_symbols > p->chunk_symbols) chunk_symbols = p->chunk_symbols;
+    chunk_symbols = std::max<int64_t>(SYM, chunk_symbols / SYM * SYM);
     const int64_t n_chunks = (p->n_symbols + chunk_symbols - 1) / chunk_symbols;
-    const uint32_t stored = outputs_of_groups(full.a.groups);
+    const size_t cplane = (size_t)p->chunk_symbols * p->pitch;
     std::vector<cudaEvent_t> up((size_t)n_chunks), done((size_t)n_chunks);
     for (auto &x : up) CU(cudaEventCreateWithFlags(&x, cudaEventDisableTiming));
     for (auto &x : done) CU(cudaEventCreateWithFlags(&x, cudaEventDisableTiming));
     CU(cudaMemcpyAsync(p->d_start, p->h_start.data(), (size_t)p->n_symbols * sizeof(int), cudaMemcpyHostToDevice, e->h2d));
     for (int64_t c = 0; c < n_chunks; ++c) {
+        const int b = (int)(c & 1);
         const int64_t s0 = c * chunk_symbols, ns = std::min(chunk_symbols, p->n_symbols - s0);
-        const size_t off = (size_t)s0 * p->pitch, bytes = (size_t)ns * p->pitch * sizeof(double);
-        for (int f = 0; f < PQB_N_FIELDS; ++f)
-            if (p->d_in[f]) CU(cudaMemcpyAsync(p->d_in[f] + off, p->h_in[f] + off, bytes, cudaMemcpyHostToDevice, e->h2d));
-        CU(cudaEventRecord(up[(size_t)c], e->h2d));
-        CU(cudaStreamWaitEvent(e->stream, up[(size_t)c], 0));
-        // a view of the panel restricted to this chunk of symbols
-        Built b = full;
-        for (int f = 0; f < PQB_N_FIELDS; ++f) b.a.in[f] = full.a.in[f] + off;
-        for (int k = 0; k < PQB_N_OUTPUTS; ++k) if (full.a.out[k]) b.a.out[k] = full.a.out[k] + off;
-        if (full.a.start) b.a.start = full.a.start + s0;
-        b.a.n_symbols = (int)ns;
-        uint32_t *bits[PQB_N_OUTPUTS];
-        for (int k = 0; k < PQB_N_OUTPUTS; ++k) bits[k] = p->d_bits[k] ? p->d_bits[k] + (size_t)s0 * p->words_per_row : nullptr;
-        for (int k = 0; k < PQB_N_OUTPUTS; ++k) {
-            if (b.a.out[k] && !(stored >> k & 1)) {
-                nan_fill_kernel<<<e->sm_count * 4, 256, 0, e->stream>>>(b.a.out[k], (size_t)ns * p->pitch);
-                CU(cudaGetLastError());
-            }
+        const size_t rows = (size_t)ns * p->pitch * sizeof(double);
+        // ---- H2D (buffer b is free once the pack of chunk c-2 has read it) ----
+        if (c >= 2) CU(cudaStreamWaitEvent(e->h2d, p->ev_packed[b], 0));
+        const double *rm_in[PQB_N_FIELDS];
+        double *tl_in[PQB_N_FIELDS];
+        int n_in = 0;
+        for (int f = 0; f < PQB_N_FIELDS; ++f) {
+            if (!p->d_in[f]) continue;
+            double *buf = p->d_xin[b] + cplane * p->in_slot[f];
+            CU(cudaMemcpyAsync(buf, p->h_in[f] + (size_t)s0 * p->pitch, rows, cudaMemcpyHostToDevice, e->h2d));
+            rm_in[n_in] = buf; tl_in[n_in] = p->d_in[f]; ++n_in;
         }
-        if ((rc = launch_suite(e, b, bits, (int)p->words_per_row, nullptr, nullptr))) return rc;
-        CU(cudaEventRecord(done[(size_t)c], e->stream));
-        CU(cudaStreamWaitEvent(e->d2h, done[(size_t)c], 0));
-        const size_t boff = (size_t)s0 * p->words_per_row, bbytes = (size_t)ns * p->words_per_row * sizeof(uint32_t);
+        CU(cudaEventRecord(up[(size_t)c], e->h2d));
+        // ---- compute ----
+        CU(cudaStreamWaitEvent(e->stream, up[(size_t)c], 0));
+        if ((rc = launch_conv(p, true, rm_in, tl_in, n_in, s0, ns, e->stream))) return rc;
+        CU(cudaEventRecord(p->ev_packed[b], e->stream));
+        if ((rc = launch_suite(p, full, s0 / SYM, (ns + SYM - 1) / SYM, nullptr, nullptr))) return rc;
+        if (c >= 2) CU(cudaStreamWaitEvent(e->stream, p->ev_d2h[b], 0));
+        const double *rm_out[PQB_N_OUTPUTS];
+        double *tl_out[PQB_N_OUTPUTS];
+        double *host_out[PQB_N_OUTPUTS];
+        int n_out = 0;
         for (int k = 0; k < PQB_N_OUTPUTS; ++k) {
             if (!full.a.out[k]) continue;
-            CU(cudaMemcpyAsync(p->h_out[k] + off, p->d_out[k] + off, bytes, cudaMemcpyDeviceToHost, e->d2h));
-            CU(cudaMemcpyAsync(p->h_bits[k] + boff, p->d_bits[k] + boff, bbytes, cudaMemcpyDeviceToHost, e->d2h));
+            rm_out[n_out] = p->d_xout[b] + cplane * p->out_slot[k]; tl_out[n_out] = p->d_out[k]; host_out[n_out] = p->h_out[k];
+            ++n_out;
         }
+        if ((rc = launch_conv(p, false, rm_out, tl_out, n_out, s0, ns, e->stream))) return rc;
+        CU(cudaEventRecord(done[(size_t)c], e->stream));
+        // ---- D2H ----
+        CU(cudaStreamWaitEvent(e->d2h, done[(size_t)c], 0));
+        for (int i = 0; i < n_out; ++i)
+            CU(cudaMemcpyAsync(host_out[i] + (size_t)s0 * p->pitch, rm_out[i], rows, cudaMemcpyDeviceToHost, e->d2h));
+        const size_t boff = (size_t)s0 * p->words_per_row, bbytes = (size_t)ns * p->words_per_row * sizeof(uint32_t);
+        for (int k = 0; k < PQB_N_OUTPUTS; ++k)
+            if (full.a.out[k]) CU(cudaMemcpyAsync(p->h_bits[k] + boff, p->d_bits[k] + boff, bbytes, cudaMemcpyDeviceToHost, e->d2h));
+        CU(cudaEventRecord(p->ev_d2h[b], e->d2h));
     }
     CU(cudaStreamSynchronize(e->d2h));
     CU(cudaStreamSynchronize(e->stream));
@@ -676,7 +777,6 @@ __device__ __forceinline__ uint64_t mix64(uint64_t z) {
     z = (z ^ (z >> 27)) * 0x94d049bb133111ebULL;
     return z ^ (z >> 31);
 }
-__device__ __forceinline__ double u01(uint64_t h) { return (double)(h >> 11) * (1.0 / 9007199254740992.0); }
 // approx N(0,1): Irwin-Hall sum of 12 uniforms built from 6 hashes (2 x 32-bit halves each)
 __device__ __forceinline__ double gauss(uint64_t key) {
     double s = 0.0;
@@ -688,42 +788,36 @@ __device__ __forceinline__ double gauss(uint64_t key) {
     return s - 6.0;
 }
 
-// 32 symbols per warp; each lane walks its symbol 32 bars at a time, the warp transposes through
-// shared memory so global writes are 256 B contiguous per row.
+// Synthetic random-walk OHLCV written straight into the tiled planes: one lane per
+// symbol walks its row; a warp writes 1 KB contiguous per plane per group.
 __global__ void __launch_bounds__(32) synth_kernel(double *c, double *h, double *l, double *v, int n_symbols,
-                                                   int n_bars, int pitch, uint64_t seed, double sigma) {
-    __shared__ double tc[32][33], th[32][33], tlo[32][33], tv[32][33];
+                                                   int n_bars, int groups, uint64_t seed, double sigma) {
     const int lane = threadIdx.x;
-    const int s0 = blockIdx.x * 32;
-    const int s = s0 + lane;
+    const int s = blockIdx.x * SYM + lane;
+    const size_t base = ((size_t)blockIdx.x * groups * SYM + lane) * GB;
     double close = 100.0;
-    for (int t0 = 0; t0 < pitch; t0 += 32) {
-        for (int j = 0; j < 32; ++j) {
-            const int t = t0 + j;
+    for (int g = 0; g < groups; ++g) {
+        double oc[4], oh[4], ol[4], ov[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int t = g * GB + k;
             const uint64_t key = (seed + (uint64_t)s) * 0x100000001b3ULL + (uint64_t)t * 4;
             const double open = close;
             close = open * exp(sigma * gauss(key));
             const double hi = fmax(open, close) * (1.0 + fabs(0.5 * sigma * gauss(key + 1)));
             const double lo = fmin(open, close) * (1.0 - fabs(0.5 * sigma * gauss(key + 2)));
             const double vol = rint(exp(13.0 + gauss(key + 3)));
-            const bool live = t < n_bars;
-            tc[lane][j] = live ? close : 0.0;
-            th[lane][j] = live ? hi : 0.0;
-            tlo[lane][j] = live ? lo : 0.0;
-            tv[lane][j] = live ? vol : 0.0;
+            const bool live = t < n_bars && s < n_symbols;
+            oc[k] = live ? close : 0.0;
+            oh[k] = live ? hi : 0.0;
+            ol[k] = live ? lo : 0.0;
+            ov[k] = live ? vol : 0.0;
         }
-        __syncwarp();
-        for (int r = 0; r < 32; ++r) {
-            const int sr = s0 + r;
-            if (sr < n_symbols && t0 + lane < pitch) {
-                const size_t o = (size_t)sr * pitch + t0 + lane;
-                if (c) c[o] = tc[r][lane];
-                if (h) h[o] = th[r][lane];
-                if (l) l[o] = tlo[r][lane];
-                if (v) v[o] = tv[r][lane];
-            }
-        }
-        __syncwarp();
+        const size_t o = base + (size_t)g * GROUP_DOUBLES;
+        if (c) *reinterpret_cast<double4 *>(c + o) = make_double4(oc[0], oc[1], oc[2], oc[3]);
+        if (h) *reinterpret_cast<double4 *>(h + o) = make_double4(oh[0], oh[1], oh[2], oh[3]);
+        if (l) *reinterpret_cast<double4 *>(l + o) = make_double4(ol[0], ol[1], ol[2], ol[3]);
+        if (v) *reinterpret_cast<double4 *>(v + o) = make_double4(ov[0], ov[1], ov[2], ov[3]);
     }
 }
 
@@ -731,16 +825,11 @@ extern "C" int pqb_panel_fill_synthetic(pqb_panel *p, uint64_t seed, double sigm
     if (!p) return fail(PQB_ERR_INVALID, "pqb_panel_fill_synthetic: NULL");
     int rc = set_dev(p->e);
     if (rc) return rc;
-    const int grid = (int)((p->n_symbols + 31) / 32);
-    synth_kernel<<<grid, 32, 0, p->e->stream>>>(p->d_in[PQB_CLOSE], p->d_in[PQB_HIGH], p->d_in[PQB_LOW],
-                                                 p->d_in[PQB_VOLUME], (int)p->n_symbols, (int)p->n_bars, (int)p->pitch,
-                                                 seed, sigma);
+    synth_kernel<<<(unsigned)p->n_blocks, 32, 0, p->e->stream>>>(p->d_in[PQB_CLOSE], p->d_in[PQB_HIGH], p->d_in[PQB_LOW],
+                                                                  p->d_in[PQB_VOLUME], (int)p->n_symbols, (int)p->n_bars,
+                                                                  (int)p->groups, seed, sigma);
     CU(cudaGetLastError());
-    if (to_host && p->staging) {
-        const size_t plane = (size_t)p->n_symbols * p->pitch * sizeof(double);
-        for (int f = 0; f < PQB_N_FIELDS; ++f)
-            if (p->d_in[f]) CU(cudaMemcpyAsync(p->h_in[f], p->d_in[f], plane, cudaMemcpyDeviceToHost, p->e->stream));
-    }
+    if (to_host && p->staging && (rc = download_planes(p, true))) return rc;
     CU(cudaStreamSynchronize(p->e->stream));
     return PQB_OK;
 }
@@ -792,8 +881,8 @@ extern "C" int pqb_suite_time_host(pqb_panel *p, const pqb_suite_params *sp, int
     if (rc) return rc;
     for (int i = 0; i < warmup; ++i)
         if ((rc = pqb_suite_run_host(p, sp, chunk_symbols))) return rc;
-    // the whole pipeline spans three streams; bracket it on the host with device-wide syncs and
-    // CUDA events on a stream that joins all three
+    // the whole pipeline spans three streams; bracket it with device-wide syncs and events on the
+    // first / last stream of the pipeline
     cudaEvent_t e0, e1;
     CU(cudaEventCreate(&e0));
     CU(cudaEventCreate(&e1));
