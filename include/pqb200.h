@@ -134,8 +134,8 @@ PQB_API void pqb_engine_destroy(pqb_engine *e);
 /* ---- panel ----------------------------------------------------------------------------
  * Host side (pinned staging, everything that crosses this ABI): row-major [symbol][pitch] f64,
  * pitch = n_bars rounded up to 16, plus Arrow LSB-first validity bitmaps per output column.
- * Device side: every plane is TILED [symbol block of 32][bar group of 4][32 symbols][4 bars]:
- * element (s, t) lives at ((s/32 * groups + t/4) * 32 + s%32) * 4 + t%4 doubles, `groups` from
+ * Device side: every plane is TILED [symbol block of 32][bar][32 symbols]:
+ * element (s, t) lives at ((s/32) * bars_padded + t) * 32 + s%32 doubles, `bars_padded` from
  * pqb_panel_tiled_shape().  Upload / download / pqb_suite_run_host convert on the device.
  * Allocates device planes for the fields in `fields_mask` (bit f = enum pqb_field f), the
  * output planes for `outputs_mask` (bit k = enum pqb_output k), output validity bitmaps and
@@ -145,8 +145,8 @@ PQB_API int pqb_panel_create(pqb_engine *e, int64_t n_symbols, int64_t n_bars, u
 PQB_API void pqb_panel_destroy(pqb_panel *p);
 PQB_API int64_t pqb_panel_pitch(const pqb_panel *p);          /* doubles per symbol row */
 PQB_API int64_t pqb_panel_validity_pitch(const pqb_panel *p); /* bytes per symbol row of a bitmap */
-/* Geometry of the tiled device planes: symbol blocks and (padded) bar groups per block. */
-PQB_API int pqb_panel_tiled_shape(const pqb_panel *p, int64_t *n_blocks, int64_t *groups);
+/* Geometry of the tiled device planes: symbol blocks and (padded) bars per block. */
+PQB_API int pqb_panel_tiled_shape(const pqb_panel *p, int64_t *n_blocks, int64_t *bars_padded);
 
 /* Copies one Arrow column (values + optional validity bitmap + bit/element offset, as in the
  * Arrow C Data Interface the reference's plugin boundary receives) into the

@@ -3,7 +3,7 @@
 // every compute entry point fails loudly when there is no device.
 //
 // Device layout: every plane (4 inputs, 21 outputs) is "tiled"
-//   [symbol block of 32][bar group of 4][32 symbols][4 bars]       (suite_kernel.cuh)
+//   [symbol block of 32][bar][32 symbols]                          (suite_kernel.cuh)
 // Host staging (pinned) and everything that crosses the ABI is row-major Arrow-style
 // [symbol][pitch] f64 + LSB-first validity bitmaps; pack_kernel / unpack_kernel convert on the
 // device, chunk by chunk, on the way in and out.
@@ -90,8 +90,8 @@ struct pqb_engine {
 struct pqb_panel {
     pqb_engine *e = nullptr;
     int64_t n_symbols = 0, n_bars = 0, pitch = 0, words_per_row = 0;
-    int64_t n_blocks = 0, groups = 0;    // tiled geometry
-    size_t plane_doubles = 0;            // n_blocks * groups * 128
+    int64_t n_blocks = 0, bars_padded = 0;   // tiled geometry
+    size_t plane_doubles = 0;            // n_blocks * bars_padded * 32
     uint32_t fields_mask = 0, outputs_mask = 0;
     double *d_in[PQB_N_FIELDS] = {};     // tiled
     double *d_out[PQB_N_OUTPUTS] = {};   // tiled
@@ -175,8 +175,8 @@ extern "C" int pqb_panel_create(pqb_engine *e, int64_t n_symbols, int64_t n_bars
     p->pitch = (n_bars + 15) / 16 * 16;
     p->words_per_row = (n_bars + 31) / 32;
     p->n_blocks = (n_symbols + SYM - 1) / SYM;
-    p->groups = ((n_bars + GB - 1) / GB + SG - 1) / SG * SG;
-    p->plane_doubles = (size_t)p->n_blocks * p->groups * GROUP_DOUBLES;
+    p->bars_padded = (n_bars + SB - 1) / SB * SB;
+    p->plane_doubles = (size_t)p->n_blocks * p->bars_padded * SYM;
     p->fields_mask = fields_mask;
     p->outputs_mask = outputs_mask;
     p->staging = host_staging != 0;
@@ -253,10 +253,10 @@ extern "C" void pqb_panel_destroy(pqb_panel *p) {
 
 extern "C" int64_t pqb_panel_pitch(const pqb_panel *p) { return p ? p->pitch : 0; }
 extern "C" int64_t pqb_panel_validity_pitch(const pqb_panel *p) { return p ? p->words_per_row * 4 : 0; }
-extern "C" int pqb_panel_tiled_shape(const pqb_panel *p, int64_t *n_blocks, int64_t *groups) {
+extern "C" int pqb_panel_tiled_shape(const pqb_panel *p, int64_t *n_blocks, int64_t *bars_padded) {
     if (!p) return fail(PQB_ERR_INVALID, "pqb_panel_tiled_shape: NULL");
     if (n_blocks) *n_blocks = p->n_blocks;
-    if (groups) *groups = p->groups;
+    if (bars_padded) *bars_padded = p->bars_padded;
     return PQB_OK;
 }
 extern "C" double *pqb_panel_host_field(pqb_panel *p, int f) {
@@ -335,9 +335,9 @@ static int launch_conv(pqb_panel *p, bool pack, const double *const *rowmajor, d
     V.n_symbols = (int)ns;
     V.n_bars = (int)p->n_bars;
     V.pitch = (int)p->pitch;
-    V.groups = (int)p->groups;
+    V.bars_padded = (int)p->bars_padded;
     V.block0 = (int)(s0 / SYM);
-    dim3 grid((unsigned)((p->groups + 7) / 8), (unsigned)((ns + SYM - 1) / SYM));
+    dim3 grid((unsigned)((p->bars_padded + 31) / 32), (unsigned)((ns + SYM - 1) / SYM));
     if (pack) pack_kernel<<<grid, 256, 0, st>>>(V);
     else unpack_kernel<<<grid, 256, 0, st>>>(V);
     CU(cudaGetLastError());
@@ -465,7 +465,7 @@ static int build_args(const pqb_panel *p, const pqb_suite_params *sp, Built *out
     A.n_symbols = (int)p->n_symbols;
     A.n_bars = n_bars;
     A.n_blocks = (int)p->n_blocks;
-    A.groups = (int)p->groups;
+    A.bars_padded = (int)p->bars_padded;
     A.block0 = 0;
 
     int steady = 1;
@@ -589,11 +589,9 @@ static int build_args(const pqb_panel *p, const pqb_suite_params *sp, Built *out
     // shared-memory rings (slots of 32 doubles)
     long long off = 0;
     auto take = [&](int slots) { const long long o = off; off += (long long)std::max(slots, 1) * SYM; return (int)std::min<long long>(o, 1ll << 30); };
-    int cmax = 0;
-    if (A.gmask & G_SMA) cmax = std::max(cmax, A.sma_p);
-    if (A.gmask & G_BB) cmax = std::max(cmax, A.bb_p);
-    if (A.gmask & G_TRIMA) cmax = std::max(cmax, A.tri_n1);
-    A.cring_slots = cmax + 1; A.off_cring = take(A.cring_slots);
+    A.sring_slots = ((A.gmask & G_SMA) ? A.sma_p : 0) + 1; A.off_sring = take(A.sring_slots);
+    A.bring_slots = ((A.gmask & G_BB) ? A.bb_p : 0) + 1; A.off_bring = take(A.bring_slots);
+    A.c1ring_slots = ((A.gmask & G_TRIMA) ? A.tri_n1 : 0) + 1; A.off_c1ring = take(A.c1ring_slots);
     A.tring_slots = ((A.gmask & G_TRIMA) ? A.tri_n2 : 0) + 1; A.off_tring = take(A.tring_slots);
     A.fk_slots = ((A.gmask & G_KDJ) ? A.kdj_sk : 0) + 1; A.off_fk = take(A.fk_slots);
     A.sk_slots = ((A.gmask & G_KDJ) ? A.kdj_sd : 0) + 1; A.off_sk = take(A.sk_slots);
@@ -645,7 +643,7 @@ static int launch_suite(pqb_panel *p, const Built &full, int64_t b0, int64_t nb,
     pqb_engine *e = p->e;
     int n_launch = 0;
     const uint32_t stored = outputs_of_groups(full.a.gmask);
-    const size_t boff = (size_t)b0 * p->groups * GROUP_DOUBLES, bn = (size_t)nb * p->groups * GROUP_DOUBLES;
+    const size_t boff = (size_t)b0 * p->bars_padded * SYM, bn = (size_t)nb * p->bars_padded * SYM;
     for (int k = 0; k < PQB_N_OUTPUTS; ++k) {
         if (full.a.out[k] && !(stored >> k & 1)) {
             nan_fill_kernel<<<e->sm_count * 4, 256, 0, e->stream>>>(full.a.out[k] + boff, bn);
@@ -789,35 +787,26 @@ __device__ __forceinline__ double gauss(uint64_t key) {
 }
 
 // Synthetic random-walk OHLCV written straight into the tiled planes: one lane per
-// symbol walks its row; a warp writes 1 KB contiguous per plane per group.
+// symbol walks its row; a warp writes 256 B contiguous per plane per bar.
 __global__ void __launch_bounds__(32) synth_kernel(double *c, double *h, double *l, double *v, int n_symbols,
-                                                   int n_bars, int groups, uint64_t seed, double sigma) {
+                                                   int n_bars, int bars_padded, uint64_t seed, double sigma) {
     const int lane = threadIdx.x;
     const int s = blockIdx.x * SYM + lane;
-    const size_t base = ((size_t)blockIdx.x * groups * SYM + lane) * GB;
+    const size_t base = (size_t)blockIdx.x * bars_padded * SYM + lane;
     double close = 100.0;
-    for (int g = 0; g < groups; ++g) {
-        double oc[4], oh[4], ol[4], ov[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int t = g * GB + k;
-            const uint64_t key = (seed + (uint64_t)s) * 0x100000001b3ULL + (uint64_t)t * 4;
-            const double open = close;
-            close = open * exp(sigma * gauss(key));
-            const double hi = fmax(open, close) * (1.0 + fabs(0.5 * sigma * gauss(key + 1)));
-            const double lo = fmin(open, close) * (1.0 - fabs(0.5 * sigma * gauss(key + 2)));
-            const double vol = rint(exp(13.0 + gauss(key + 3)));
-            const bool live = t < n_bars && s < n_symbols;
-            oc[k] = live ? close : 0.0;
-            oh[k] = live ? hi : 0.0;
-            ol[k] = live ? lo : 0.0;
-            ov[k] = live ? vol : 0.0;
-        }
-        const size_t o = base + (size_t)g * GROUP_DOUBLES;
-        if (c) *reinterpret_cast<double4 *>(c + o) = make_double4(oc[0], oc[1], oc[2], oc[3]);
-        if (h) *reinterpret_cast<double4 *>(h + o) = make_double4(oh[0], oh[1], oh[2], oh[3]);
-        if (l) *reinterpret_cast<double4 *>(l + o) = make_double4(ol[0], ol[1], ol[2], ol[3]);
-        if (v) *reinterpret_cast<double4 *>(v + o) = make_double4(ov[0], ov[1], ov[2], ov[3]);
+    for (int t = 0; t < bars_padded; ++t) {
+        const uint64_t key = (seed + (uint64_t)s) * 0x100000001b3ULL + (uint64_t)t * 4;
+        const double open = close;
+        close = open * exp(sigma * gauss(key));
+        const double hi = fmax(open, close) * (1.0 + fabs(0.5 * sigma * gauss(key + 1)));
+        const double lo = fmin(open, close) * (1.0 - fabs(0.5 * sigma * gauss(key + 2)));
+        const double vol = rint(exp(13.0 + gauss(key + 3)));
+        const bool live = t < n_bars && s < n_symbols;
+        const size_t o = base + (size_t)t * SYM;
+        if (c) c[o] = live ? close : 0.0;
+        if (h) h[o] = live ? hi : 0.0;
+        if (l) l[o] = live ? lo : 0.0;
+        if (v) v[o] = live ? vol : 0.0;
     }
 }
 
@@ -827,7 +816,7 @@ extern "C" int pqb_panel_fill_synthetic(pqb_panel *p, uint64_t seed, double sigm
     if (rc) return rc;
     synth_kernel<<<(unsigned)p->n_blocks, 32, 0, p->e->stream>>>(p->d_in[PQB_CLOSE], p->d_in[PQB_HIGH], p->d_in[PQB_LOW],
                                                                   p->d_in[PQB_VOLUME], (int)p->n_symbols, (int)p->n_bars,
-                                                                  (int)p->groups, seed, sigma);
+                                                                  (int)p->bars_padded, seed, sigma);
     CU(cudaGetLastError());
     if (to_host && p->staging && (rc = download_planes(p, true))) return rc;
     CU(cudaStreamSynchronize(p->e->stream));
