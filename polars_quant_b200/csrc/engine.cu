@@ -141,8 +141,10 @@ extern "C" int pqb_engine_create(int device, pqb_engine **out) {
     CU(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&e->h2d, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&e->d2h, cudaStreamNonBlocking));
-    CU(cudaFuncSetAttribute(suite_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
-    CU(cudaFuncSetAttribute(suite_fused_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    CU(cudaFuncSetAttribute(suite_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+    CU(cudaFuncSetAttribute(suite_fused_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    CU(cudaFuncSetAttribute(suite_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+    CU(cudaFuncSetAttribute(suite_fused_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     *out = e;
     return PQB_OK;
 }
@@ -589,15 +591,16 @@ static int build_args(const pqb_panel *p, const pqb_suite_params *sp, Built *out
     // shared-memory rings (slots of 32 doubles)
     long long off = 0;
     auto take = [&](int slots) { const long long o = off; off += (long long)std::max(slots, 1) * SYM; return (int)std::min<long long>(o, 1ll << 30); };
-    A.sring_slots = ((A.gmask & G_SMA) ? A.sma_p : 0) + 1; A.off_sring = take(A.sring_slots);
-    A.bring_slots = ((A.gmask & G_BB) ? A.bb_p : 0) + 1; A.off_bring = take(A.bring_slots);
-    A.c1ring_slots = ((A.gmask & G_TRIMA) ? A.tri_n1 : 0) + 1; A.off_c1ring = take(A.c1ring_slots);
-    A.tring_slots = ((A.gmask & G_TRIMA) ? A.tri_n2 : 0) + 1; A.off_tring = take(A.tring_slots);
-    A.fk_slots = ((A.gmask & G_KDJ) ? A.kdj_sk : 0) + 1; A.off_fk = take(A.fk_slots);
-    A.sk_slots = ((A.gmask & G_KDJ) ? A.kdj_sd : 0) + 1; A.off_sk = take(A.sk_slots);
-    const int wp = (A.gmask & G_WILLR) ? A.willr_p : 0;
-    const int mp = ((A.gmask & G_MIDPRICE) && !((A.gmask & G_WILLR) && A.willr_p == A.mid_p)) ? A.mid_p : 0;
-    const int kp = (A.gmask & G_KDJ) ? A.kdj_k : 0;
+    A.sring_slots = (A.gmask & G_SMA) ? A.sma_p : 1; A.off_sring = take(A.sring_slots);
+    A.bring_slots = (A.gmask & G_BB) ? A.bb_p : 1; A.off_bring = take(A.bring_slots);
+    A.c1ring_slots = (A.gmask & G_TRIMA) ? A.tri_n1 : 1; A.off_c1ring = take(A.c1ring_slots);
+    A.tring_slots = (A.gmask & G_TRIMA) ? A.tri_n2 : 1; A.off_tring = take(A.tring_slots);
+    A.fk_slots = (A.gmask & G_KDJ) ? A.kdj_sk : 1; A.off_fk = take(A.fk_slots);
+    A.sk_slots = (A.gmask & G_KDJ) ? A.kdj_sd : 1; A.off_sk = take(A.sk_slots);
+    // van Herk arrays: p slots + 1 sentinel each
+    const int wp = (A.gmask & G_WILLR) ? A.willr_p + 1 : 0;
+    const int mp = ((A.gmask & G_MIDPRICE) && !((A.gmask & G_WILLR) && A.willr_p == A.mid_p)) ? A.mid_p + 1 : 0;
+    const int kp = (A.gmask & G_KDJ) ? A.kdj_k + 1 : 0;
     A.off_wh = take(wp); A.off_wl = take(wp);
     A.off_mh = take(mp); A.off_ml = take(mp);
     A.off_kh = take(kp); A.off_kl = take(kp);
@@ -654,7 +657,10 @@ static int launch_suite(pqb_panel *p, const Built &full, int64_t b0, int64_t nb,
     if (full.a.gmask) {
         SuiteArgs a = full.a;
         a.block0 = (int)b0;
-        suite_fused_kernel<<<(unsigned)nb, CTA_THREADS, a.smem_bytes, e->stream>>>(a);
+        bool fulls = a.gmask == G_ALL;
+        for (int k = 0; k < PQB_N_OUTPUTS; ++k) fulls &= a.out[k] != nullptr;
+        if (fulls) suite_fused_kernel<true><<<(unsigned)nb, CTA_THREADS, a.smem_bytes, e->stream>>>(a);
+        else suite_fused_kernel<false><<<(unsigned)nb, CTA_THREADS, a.smem_bytes, e->stream>>>(a);
         CU(cudaGetLastError());
         ++n_launch;
     }
