@@ -14,6 +14,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -613,6 +614,8 @@ static int build_args(const pqb_panel *p, const pqb_suite_params *sp, Built *out
     return PQB_OK;
 }
 
+static unsigned long long *g_dbg = nullptr;   // PQB_DEBUG_CLOCKS tuning aid
+
 // NaN fill for all-null columns (period 0)
 __global__ void nan_fill_kernel(double *p, size_t n) {
     const double nn = __longlong_as_double(0x7ff8000000000000LL);
@@ -657,12 +660,23 @@ static int launch_suite(pqb_panel *p, const Built &full, int64_t b0, int64_t nb,
     if (full.a.gmask) {
         SuiteArgs a = full.a;
         a.block0 = (int)b0;
+        const bool want_dbg = getenv("PQB_DEBUG_CLOCKS") != nullptr;    // tuning aid: per-role busy cycles
+        if (want_dbg && !g_dbg) CU(cudaMalloc(&g_dbg, N_ROLES * sizeof(unsigned long long)));
+        a.dbg = want_dbg ? g_dbg : nullptr;
         bool fulls = a.gmask == G_ALL;
         for (int k = 0; k < PQB_N_OUTPUTS; ++k) fulls &= a.out[k] != nullptr;
         if (fulls) suite_fused_kernel<true><<<(unsigned)nb, CTA_THREADS, a.smem_bytes, e->stream>>>(a);
         else suite_fused_kernel<false><<<(unsigned)nb, CTA_THREADS, a.smem_bytes, e->stream>>>(a);
         CU(cudaGetLastError());
         ++n_launch;
+    }
+    if (g_dbg && full.a.gmask && getenv("PQB_DEBUG_CLOCKS")) {
+        unsigned long long h[N_ROLES];
+        CU(cudaStreamSynchronize(e->stream));
+        CU(cudaMemcpy(h, g_dbg, sizeof h, cudaMemcpyDeviceToHost));
+        fprintf(stderr, "[pqb] busy cycles/bar by role (block %lld):", (long long)b0);
+        for (int r = 0; r < N_ROLES; ++r) fprintf(stderr, " r%d=%.0f", r, (double)h[r] / (double)p->n_bars);
+        fprintf(stderr, "\n");
     }
     if (ev_after_fused) CU(cudaEventRecord(ev_after_fused, e->stream));
     const int64_t s0 = b0 * SYM, ns = std::min<int64_t>(nb * SYM, p->n_symbols - s0);
