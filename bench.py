@@ -55,30 +55,68 @@ def measured_peak():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region."""
+    """SM clock / throttle reasons sampled DURING the timed region: NVML in-process every ~5 ms
+    (nvidia_ml_py), falling back to polling nvidia-smi."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index: int):
         self.gpu = gpu_index
-        self.rows = []
+        self.sm, self.mx, self.reasons = [], [], set()
         self._stop = threading.Event()
         self._t = None
+        self._nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+            self._nvml = pynvml
+        except Exception:
+            self._nvml = None
 
-    def _run(self):
+    def _run_nvml(self):
+        nv = self._nvml
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+            getattr(nv, "nvmlDeviceGetCurrentClocksThrottleReasons")
+        try:
+            mx = float(nv.nvmlDeviceGetMaxClockInfo(self._h, nv.NVML_CLOCK_SM))
+        except Exception:
+            mx = None
+        while not self._stop.is_set():
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)))
+                if mx:
+                    self.mx.append(mx)
+                r = int(get_reasons(self._h))
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            self._stop.wait(0.005)
+
+    def _run_smi(self):
         while not self._stop.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
                                       "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
                 for line in out.strip().splitlines():
-                    self.rows.append([c.strip() for c in line.split(",")])
+                    r = [c.strip() for c in line.split(",")]
+                    self.sm.append(float(r[1])); self.mx.append(float(r[2]))
+                    for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                        if v.lower().startswith("active"):
+                            self.reasons.add(name)
             except Exception:
                 pass
-            self._stop.wait(0.1)
+            self._stop.wait(0.05)
 
     def __enter__(self):
-        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t = threading.Thread(target=self._run_nvml if self._nvml else self._run_smi, daemon=True)
         self._t.start()
         return self
 
@@ -87,19 +125,11 @@ class ClockSampler:
         self._t.join(timeout=6)
 
     def summary(self):
-        sm, mx, reasons = [], [], set()
-        for r in self.rows:
-            try:
-                sm.append(float(r[1])); mx.append(float(r[2]))
-            except Exception:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        if not sm:
+        if not self.sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
-                "samples": len(sm)}
+        return {"sm_mhz": float(np.median(self.sm)), "sm_max_mhz": float(max(self.mx)) if self.mx else None,
+                "reasons": sorted(self.reasons), "samples": len(self.sm),
+                "source": "nvml" if self._nvml else "nvidia-smi"}
 
 
 def cpu_suite_rate(c, h, l, v, threads: int, budget_s: float):
@@ -241,9 +271,8 @@ def main():
                "h2d_bytes_per_step": int(N_IN * Se * pitch * 8 + Se * 4),
                "d2h_bytes_per_step": int(N_OUT * Se * pitch * 8 + N_OUT * Se * hp.validity_pitch),
                "symbols": Se, "bars": N, "ms_per_step": ms_host / args.e2e_steps,
-               "note": "pinned host panel -> chunked H2D || fused suite || D2H on 3 streams; PCIe-bound"}
-        chunks = -(-Se // (engine_sm_count(engine) * 8))
-        e2e_launches = launches * chunks * args.e2e_steps
+               "note": "row-major pinned host panel -> chunked H2D || pack + fused suite + unpack || D2H on 3 streams; PCIe-bound"}
+        e2e_launches = hp.last_launches() * args.e2e_steps
 
         # ---- CPU baseline on rank 0: the oracle port over a bounded sample of the same panel ----
         cpu = None
@@ -277,7 +306,7 @@ def main():
                        % (ALGO_BYTES_PER_SYMBOL_BAR * S * N / 1e9),
                        "parallelism": "symbols sharded per GPU, no collective"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": "suite_fused_kernel<32>", "peak_source": peak_src,
+                         "traffic": traffic, "kernel": "suite_fused_kernel<true>", "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": ALGO_BYTES_PER_SYMBOL_BAR * S * N,
                          "kernel_ms": fused_ms_avg},
             "cpu_baseline": cpu,
@@ -290,9 +319,6 @@ def main():
     if dist is not None:
         dist.destroy_process_group()
 
-
-def engine_sm_count(engine) -> int:
-    return 148
 
 
 if __name__ == "__main__":

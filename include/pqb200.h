@@ -247,6 +247,8 @@ PQB_API int pqb_suite_time(pqb_panel *p, const pqb_suite_params *params, int war
 /* Same for the end-to-end host path (pqb_suite_run_host); ms includes H2D + kernels + D2H. */
 PQB_API int pqb_suite_time_host(pqb_panel *p, const pqb_suite_params *params, int64_t chunk_symbols,
                         int warmup, int iters, float *ms_total);
+/* Kernels launched by the most recent pqb_suite_run / pqb_suite_run_host on this panel. */
+PQB_API int pqb_panel_last_launches(const pqb_panel *p);
 /* Writes > L2-size bytes to a scratch buffer (L2 flush between timed iterations). */
 PQB_API int pqb_flush_l2(pqb_engine *e);
 

@@ -112,6 +112,7 @@ struct pqb_panel {
     int n_in_alloc = 0, n_out_alloc = 0;
     int in_slot[PQB_N_FIELDS] = {}, out_slot[PQB_N_OUTPUTS] = {};
     cudaEvent_t ev_packed[2] = {}, ev_d2h[2] = {};
+    int last_launches = 0;               // kernels launched by the most recent run / run_host
 };
 
 static int set_dev(const pqb_engine *e) {
@@ -614,7 +615,9 @@ static int build_args(const pqb_panel *p, const pqb_suite_params *sp, Built *out
     return PQB_OK;
 }
 
-static unsigned long long *g_dbg = nullptr;   // PQB_DEBUG_CLOCKS tuning aid
+#ifdef PQB_DEBUG_CLOCKS
+static unsigned long long *g_dbg = nullptr;
+#endif
 
 // NaN fill for all-null columns (period 0)
 __global__ void nan_fill_kernel(double *p, size_t n) {
@@ -660,9 +663,12 @@ static int launch_suite(pqb_panel *p, const Built &full, int64_t b0, int64_t nb,
     if (full.a.gmask) {
         SuiteArgs a = full.a;
         a.block0 = (int)b0;
-        const bool want_dbg = getenv("PQB_DEBUG_CLOCKS") != nullptr;    // tuning aid: per-role busy cycles
-        if (want_dbg && !g_dbg) CU(cudaMalloc(&g_dbg, N_ROLES * sizeof(unsigned long long)));
-        a.dbg = want_dbg ? g_dbg : nullptr;
+#ifdef PQB_DEBUG_CLOCKS      // tuning build: per-role busy cycles of the first block (costs ~18% on config 4)
+        if (!g_dbg) CU(cudaMalloc(&g_dbg, N_ROLES * sizeof(unsigned long long)));
+        a.dbg = g_dbg;
+#else
+        a.dbg = nullptr;
+#endif
         bool fulls = a.gmask == G_ALL;
         for (int k = 0; k < PQB_N_OUTPUTS; ++k) fulls &= a.out[k] != nullptr;
         if (fulls) suite_fused_kernel<true><<<(unsigned)nb, CTA_THREADS, a.smem_bytes, e->stream>>>(a);
@@ -670,7 +676,8 @@ static int launch_suite(pqb_panel *p, const Built &full, int64_t b0, int64_t nb,
         CU(cudaGetLastError());
         ++n_launch;
     }
-    if (g_dbg && full.a.gmask && getenv("PQB_DEBUG_CLOCKS")) {
+#ifdef PQB_DEBUG_CLOCKS
+    if (g_dbg && full.a.gmask) {
         unsigned long long h[N_ROLES];
         CU(cudaStreamSynchronize(e->stream));
         CU(cudaMemcpy(h, g_dbg, sizeof h, cudaMemcpyDeviceToHost));
@@ -678,6 +685,7 @@ static int launch_suite(pqb_panel *p, const Built &full, int64_t b0, int64_t nb,
         for (int r = 0; r < N_ROLES; ++r) fprintf(stderr, " r%d=%.0f", r, (double)h[r] / (double)p->n_bars);
         fprintf(stderr, "\n");
     }
+#endif
     if (ev_after_fused) CU(cudaEventRecord(ev_after_fused, e->stream));
     const int64_t s0 = b0 * SYM, ns = std::min<int64_t>(nb * SYM, p->n_symbols - s0);
     ValidityArgs V{};
@@ -708,7 +716,11 @@ static int run_suite(pqb_panel *p, const pqb_suite_params *sp, cudaEvent_t ev_af
     if (rc) return rc;
     Built b;
     if ((rc = build_args(p, sp, &b))) return rc;
-    return launch_suite(p, b, 0, p->n_blocks, ev_after_fused, launches);
+    int nl = 0;
+    rc = launch_suite(p, b, 0, p->n_blocks, ev_after_fused, &nl);
+    p->last_launches = nl;
+    if (launches) *launches = nl;
+    return rc;
 }
 
 extern "C" int pqb_suite_run(pqb_panel *p, const pqb_suite_params *sp) { return run_suite(p, sp, nullptr, nullptr); }
@@ -736,6 +748,7 @@ extern "C" int pqb_suite_run_host(pqb_panel *p, const pqb_suite_params *sp, int6
     for (auto &x : up) CU(cudaEventCreateWithFlags(&x, cudaEventDisableTiming));
     for (auto &x : done) CU(cudaEventCreateWithFlags(&x, cudaEventDisableTiming));
     CU(cudaMemcpyAsync(p->d_start, p->h_start.data(), (size_t)p->n_symbols * sizeof(int), cudaMemcpyHostToDevice, e->h2d));
+    int total_launches = 0;
     for (int64_t c = 0; c < n_chunks; ++c) {
         const int b = (int)(c & 1);
         const int64_t s0 = c * chunk_symbols, ns = std::min(chunk_symbols, p->n_symbols - s0);
@@ -756,7 +769,9 @@ extern "C" int pqb_suite_run_host(pqb_panel *p, const pqb_suite_params *sp, int6
         CU(cudaStreamWaitEvent(e->stream, up[(size_t)c], 0));
         if ((rc = launch_conv(p, true, rm_in, tl_in, n_in, s0, ns, e->stream))) return rc;
         CU(cudaEventRecord(p->ev_packed[b], e->stream));
-        if ((rc = launch_suite(p, full, s0 / SYM, (ns + SYM - 1) / SYM, nullptr, nullptr))) return rc;
+        int nl = 0;
+        if ((rc = launch_suite(p, full, s0 / SYM, (ns + SYM - 1) / SYM, nullptr, &nl))) return rc;
+        total_launches += nl + (n_in ? 1 : 0);
         if (c >= 2) CU(cudaStreamWaitEvent(e->stream, p->ev_d2h[b], 0));
         const double *rm_out[PQB_N_OUTPUTS];
         double *tl_out[PQB_N_OUTPUTS];
@@ -768,6 +783,7 @@ extern "C" int pqb_suite_run_host(pqb_panel *p, const pqb_suite_params *sp, int6
             ++n_out;
         }
         if ((rc = launch_conv(p, false, rm_out, tl_out, n_out, s0, ns, e->stream))) return rc;
+        total_launches += n_out ? 1 : 0;
         CU(cudaEventRecord(done[(size_t)c], e->stream));
         // ---- D2H ----
         CU(cudaStreamWaitEvent(e->d2h, done[(size_t)c], 0));
@@ -783,8 +799,11 @@ extern "C" int pqb_suite_run_host(pqb_panel *p, const pqb_suite_params *sp, int6
     CU(cudaStreamSynchronize(e->h2d));
     for (auto &x : up) cudaEventDestroy(x);
     for (auto &x : done) cudaEventDestroy(x);
+    p->last_launches = total_launches;
     return PQB_OK;
 }
+
+extern "C" int pqb_panel_last_launches(const pqb_panel *p) { return p ? p->last_launches : 0; }
 
 // ---------------------------------------------------------------------------------------
 // measurement helpers

@@ -156,6 +156,15 @@ class Panel:
                 res[name] = (self.host_output(k), self.host_validity(k))
         return res
 
+    def last_launches(self) -> int:
+        return N.lib().pqb_panel_last_launches(self._h)
+
+    def tiled_shape(self):
+        """(symbol blocks, padded bars per block) of the tiled device planes."""
+        nb, bp = C.c_int64(), C.c_int64()
+        N.check(N.lib().pqb_panel_tiled_shape(self._h, C.byref(nb), C.byref(bp)))
+        return nb.value, bp.value
+
     # ---- measurement ----
     def time_device(self, params=None, warmup: int = 3, iters: int = 20):
         params = params or N.default_params()
