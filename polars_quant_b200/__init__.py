@@ -2,5 +2,6 @@
 wide `{symbol}_{column}` f64 panels.  CUDA (sm_100a) behind a C ABI; no CPU fallback."""
 from . import _native
 from .panel import Engine, Panel, get_engine
+from . import shard
 
-__all__ = ["Engine", "Panel", "get_engine", "_native"]
+__all__ = ["Engine", "Panel", "get_engine", "shard", "_native"]

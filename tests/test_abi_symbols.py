@@ -1,0 +1,67 @@
+"""The C-ABI library loads on a machine without a GPU, exports every symbol include/pqb200.h
+declares, and fails loudly (PQB_ERR_NO_DEVICE) instead of falling back when there is no device."""
+import ctypes as C
+import re
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from polars_quant_b200 import _native
+    _native.build()
+    return _native.lib()
+
+
+def declared_functions():
+    text = (ROOT / "include" / "pqb200.h").read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"PQB_API\s+[\w\s\*]+?\b(pqb_\w+)\s*\(", text)))
+
+
+def test_header_declares_the_expected_surface():
+    names = declared_functions()
+    for must in ("pqb_engine_create", "pqb_panel_create", "pqb_panel_set_column", "pqb_suite_run",
+                 "pqb_suite_run_host", "pqb_panel_get_output", "pqb_sma", "pqb_ema", "pqb_tema", "pqb_trima",
+                 "pqb_ma", "pqb_bbands", "pqb_macd", "pqb_rsi", "pqb_trange", "pqb_atr", "pqb_natr", "pqb_obv",
+                 "pqb_ad", "pqb_stoch", "pqb_kdj", "pqb_willr", "pqb_midprice", "pqb_last_error"):
+        assert must in names
+    assert len(names) >= 40
+
+
+def test_library_exports_every_declared_symbol(lib):
+    missing = [n for n in declared_functions() if not hasattr(lib, n)]
+    assert not missing, missing
+
+
+def test_no_cpu_fallback_without_a_device(lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    assert lib.pqb_abi_version() == 1
+    assert lib.pqb_device_count() == 0
+    h = C.c_void_p()
+    rc = lib.pqb_engine_create(0, C.byref(h))
+    assert rc == -1 and not h.value                      # PQB_ERR_NO_DEVICE
+    assert b"no CPU fallback" in lib.pqb_last_error()
+
+
+def test_default_params_are_the_reference_python_defaults(lib):
+    from polars_quant_b200 import _native as N
+    p = N.default_params()
+    assert (p.sma_period, p.ema_period, p.tema_period, p.trima_period) == (30, 30, 30, 30)     # overlap.py
+    assert (p.bbands_period, p.bbands_nbdevup, p.bbands_nbdevdn) == (20, 2.0, 2.0)
+    assert (p.macd_fast, p.macd_slow, p.macd_signal, p.rsi_period) == (12, 26, 9, 14)           # momentum.py
+    assert (p.atr_period, p.natr_period, p.willr_period, p.midprice_period) == (14, 14, 14, 14)
+    assert (p.kdj_fastk, p.kdj_slowk, p.kdj_slowd) == (9, 3, 3)
+    assert p.indicators == N.IND_ALL
+
+
+def test_product_never_imports_the_oracle():
+    """Only tests/, __graft_entry__.smoke() and bench.py may touch oracle/."""
+    for f in (ROOT / "polars_quant_b200").rglob("*"):
+        if f.suffix in (".py", ".cu", ".cuh", ".h") and f.is_file():
+            assert "oracle" not in f.read_text().replace("the oracle", "").replace("oracle's", ""), f
