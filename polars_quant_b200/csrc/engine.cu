@@ -74,7 +74,7 @@ extern "C" void pqb_suite_params_default(pqb_suite_params *p) {
 // engine / panel objects
 // ---------------------------------------------------------------------------------------
 static constexpr int kMaxSmem = 227 * 1024;      // opt-in dynamic shared memory per CTA on sm_100
-static constexpr int kFixedSmem = NS * STAGE_DOUBLES * 8 + 2 * NS * 8;   // TMA stages + mbarriers
+static constexpr int kFixedSmem = NS * STAGE_BYTES + 2 * NS * 8;   // TMA stages (+ validity words) + mbarriers
 
 struct pqb_engine {
     int device = 0;
@@ -113,6 +113,17 @@ struct pqb_panel {
     int in_slot[PQB_N_FIELDS] = {}, out_slot[PQB_N_OUTPUTS] = {};
     cudaEvent_t ev_packed[2] = {}, ev_d2h[2] = {};
     int last_launches = 0;               // kernels launched by the most recent run / run_host
+    // null-aware mode (allocated on first use)
+    std::vector<int32_t> h_start_explicit;              // pqb_panel_set_starts
+    std::vector<int32_t> h_lead[PQB_N_FIELDS];          // leading nulls seen by pqb_panel_set_column (-1: none given)
+    std::vector<uint32_t> h_vin[PQB_N_FIELDS];          // row-major input validity bitmaps (empty: all valid)
+    std::vector<uint8_t> h_flags;                       // per symbol: bit f = field f has an interior/trailing null
+    bool has_interior = false;
+    bool nulls_mode = false;                            // decided by prepare_nulls()
+    uint32_t *d_vin[PQB_N_FIELDS] = {};                 // row-major bitmaps on the device
+    uint32_t *d_vmask = nullptr;                        // tiled [block][bar][4]
+    uint32_t *d_ovm[PQB_N_OUTPUTS] = {};                // tiled [block][bar] per output
+    uint8_t *d_flags = nullptr;
 };
 
 static int set_dev(const pqb_engine *e) {
@@ -143,10 +154,12 @@ extern "C" int pqb_engine_create(int device, pqb_engine **out) {
     CU(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&e->h2d, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&e->d2h, cudaStreamNonBlocking));
-    CU(cudaFuncSetAttribute(suite_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
-    CU(cudaFuncSetAttribute(suite_fused_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    CU(cudaFuncSetAttribute(suite_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
-    CU(cudaFuncSetAttribute(suite_fused_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    CU(cudaFuncSetAttribute(suite_fused_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+    CU(cudaFuncSetAttribute(suite_fused_kernel<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    CU(cudaFuncSetAttribute(suite_fused_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+    CU(cudaFuncSetAttribute(suite_fused_kernel<false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    CU(cudaFuncSetAttribute(suite_fused_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+    CU(cudaFuncSetAttribute(suite_fused_kernel<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     *out = e;
     return PQB_OK;
 }
@@ -233,6 +246,9 @@ extern "C" int pqb_panel_create(pqb_engine *e, int64_t n_symbols, int64_t n_bars
     if ((ce = cudaMalloc(&p->d_start, (size_t)p->n_blocks * SYM * sizeof(int))) != cudaSuccess) return bail(ce, "cudaMalloc(start)");
     if ((ce = cudaMemsetAsync(p->d_start, 0, (size_t)p->n_blocks * SYM * sizeof(int), e->stream)) != cudaSuccess) return bail(ce, "memset");
     p->h_start.assign((size_t)n_symbols, 0);
+    p->h_start_explicit.assign((size_t)n_symbols, 0);
+    for (auto &v : p->h_lead) v.assign((size_t)n_symbols, -1);
+    p->h_flags.assign((size_t)n_symbols, 0);
     if ((ce = cudaStreamSynchronize(e->stream)) != cudaSuccess) return bail(ce, "sync");
     *out = p;
     return PQB_OK;
@@ -247,6 +263,10 @@ extern "C" void pqb_panel_destroy(pqb_panel *p) {
     for (auto &q : p->d_xin) if (q) cudaFree(q);
     for (auto &q : p->d_xout) if (q) cudaFree(q);
     if (p->d_start) cudaFree(p->d_start);
+    for (auto &q : p->d_vin) if (q) cudaFree(q);
+    for (auto &q : p->d_ovm) if (q) cudaFree(q);
+    if (p->d_vmask) cudaFree(p->d_vmask);
+    if (p->d_flags) cudaFree(p->d_flags);
     for (auto &q : p->h_in) if (q) cudaFreeHost(q);
     for (auto &q : p->h_out) if (q) cudaFreeHost(q);
     for (auto &q : p->h_bits) if (q) cudaFreeHost(q);
@@ -293,36 +313,94 @@ extern "C" int pqb_panel_set_column(pqb_panel *p, int64_t symbol, int field, con
     if (len != p->n_bars || offset < 0)
         return fail(PQB_ERR_INVALID, "pqb_panel_set_column: len %lld != n_bars %lld", (long long)len, (long long)p->n_bars);
     int64_t lead = 0;
+    bool interior = false;
     if (validity) {
         while (lead < len && !bit_at(validity, offset + lead)) ++lead;
         for (int64_t i = lead; i < len; ++i)
-            if (!bit_at(validity, offset + i))
-                return fail(PQB_ERR_UNSUPPORTED,
-                            "pqb_panel_set_column: symbol %lld field %d has a null at %lld after its first valid bar "
-                            "(interior/trailing nulls are not supported by the panel path)",
-                            (long long)symbol, field, (long long)i);
+            if (!bit_at(validity, offset + i)) { interior = true; break; }
     }
     double *dst = p->h_in[field] + (size_t)symbol * p->pitch;
     memcpy(dst, values + offset, (size_t)len * sizeof(double));
-    for (int64_t i = 0; i < lead; ++i) dst[i] = 0.0;
     for (int64_t i = len; i < p->pitch; ++i) dst[i] = 0.0;
-    if (lead > p->h_start[(size_t)symbol]) { p->h_start[(size_t)symbol] = (int32_t)lead; p->starts_nonzero = true; }
+    // validity bitmap of this column (kept for the null-aware mode); null slots get a benign value so
+    // that they never drive a division through its slow path
+    auto &vin = p->h_vin[field];
+    if (validity || !vin.empty()) {
+        if (vin.empty()) vin.assign((size_t)p->n_symbols * p->words_per_row, 0xffffffffu);
+        uint32_t *row = vin.data() + (size_t)symbol * p->words_per_row;
+        for (int64_t w = 0; w < p->words_per_row; ++w) {
+            uint32_t word = 0;
+            for (int j = 0; j < 32; ++j) {
+                const int64_t i = w * 32 + j;
+                if (i < len && (!validity || bit_at(validity, offset + i))) word |= 1u << j;
+            }
+            row[w] = word;
+        }
+        if (validity)
+            for (int64_t i = 0; i < len; ++i)
+                if (!bit_at(validity, offset + i)) dst[i] = 1.0;
+    }
+    p->h_lead[field][(size_t)symbol] = validity ? (int32_t)lead : 0;
+    if (interior) { p->has_interior = true; p->h_flags[(size_t)symbol] |= (uint8_t)(1u << field); }
+    else p->h_flags[(size_t)symbol] &= (uint8_t)~(1u << field);
     return PQB_OK;
 }
 
 extern "C" int pqb_panel_set_starts(pqb_panel *p, const int32_t *starts) {
     if (!p || !starts) return fail(PQB_ERR_INVALID, "pqb_panel_set_starts: NULL argument");
-    p->starts_nonzero = false;
     for (int64_t s = 0; s < p->n_symbols; ++s) {
         if (starts[s] < 0) return fail(PQB_ERR_INVALID, "pqb_panel_set_starts: negative start");
-        p->h_start[(size_t)s] = (int32_t)std::min<int64_t>(starts[s], p->n_bars);
-        if (starts[s]) p->starts_nonzero = true;
+        p->h_start_explicit[(size_t)s] = (int32_t)std::min<int64_t>(starts[s], p->n_bars);
     }
-    int rc = set_dev(p->e);
-    if (rc) return rc;
-    CU(cudaMemcpyAsync(p->d_start, p->h_start.data(), (size_t)p->n_symbols * sizeof(int), cudaMemcpyHostToDevice,
-                       p->e->stream));
-    CU(cudaStreamSynchronize(p->e->stream));
+    return PQB_OK;
+}
+
+// Decides between the plain mode (every symbol valid on [start, n_bars), all fields alike) and the
+// null-aware mode (per-bar validity words), and ships starts / masks / flags to the device.
+static int prepare_nulls(pqb_panel *p, cudaStream_t st) {
+    bool nulls = p->has_interior;
+    for (size_t s = 0; s < (size_t)p->n_symbols && !nulls; ++s) {
+        int32_t lead = -2;
+        for (int f = 0; f < PQB_N_FIELDS; ++f) {
+            if (!p->d_in[f] || p->h_lead[f][s] < 0) continue;
+            if (lead == -2) lead = p->h_lead[f][s];
+            else if (lead != p->h_lead[f][s]) nulls = true;      // fields of one symbol start at different rows
+        }
+    }
+    p->nulls_mode = nulls;
+    p->starts_nonzero = false;
+    for (size_t s = 0; s < (size_t)p->n_symbols; ++s) {
+        int32_t a = p->h_start_explicit[s];
+        if (!nulls)
+            for (int f = 0; f < PQB_N_FIELDS; ++f)
+                if (p->d_in[f]) a = std::max(a, p->h_lead[f][s]);
+        p->h_start[s] = a;
+        if (a) p->starts_nonzero = true;
+    }
+    CU(cudaMemcpyAsync(p->d_start, p->h_start.data(), (size_t)p->n_symbols * sizeof(int), cudaMemcpyHostToDevice, st));
+    if (!nulls) return PQB_OK;
+    const size_t bplane = (size_t)p->n_symbols * p->words_per_row * sizeof(uint32_t);
+    const size_t mwords = (size_t)p->n_blocks * p->bars_padded;
+    if (!p->d_vmask) CU(cudaMalloc(&p->d_vmask, mwords * N_IN * sizeof(uint32_t)));
+    if (!p->d_flags) CU(cudaMalloc(&p->d_flags, (size_t)p->n_blocks * SYM));
+    CU(cudaMemsetAsync(p->d_flags, 0, (size_t)p->n_blocks * SYM, st));
+    CU(cudaMemcpyAsync(p->d_flags, p->h_flags.data(), (size_t)p->n_symbols, cudaMemcpyHostToDevice, st));
+    MaskArgs V{};
+    for (int f = 0; f < PQB_N_FIELDS; ++f) {
+        if (p->h_vin[f].empty()) continue;
+        if (!p->d_vin[f]) CU(cudaMalloc(&p->d_vin[f], bplane));
+        CU(cudaMemcpyAsync(p->d_vin[f], p->h_vin[f].data(), bplane, cudaMemcpyHostToDevice, st));
+        V.rm[f] = p->d_vin[f];
+    }
+    for (int k = 0; k < PQB_N_OUTPUTS; ++k)
+        if (p->d_out[k] && !p->d_ovm[k]) CU(cudaMalloc(&p->d_ovm[k], mwords * sizeof(uint32_t)));
+    V.tiled_out = p->d_vmask;
+    V.start = p->starts_nonzero ? p->d_start : nullptr;
+    V.n_symbols = (int)p->n_symbols; V.n_bars = (int)p->n_bars; V.bars_padded = (int)p->bars_padded;
+    V.words_per_row = (int)p->words_per_row; V.n_blocks = (int)p->n_blocks;
+    dim3 grid((unsigned)((p->bars_padded + 31) / 32), (unsigned)p->n_blocks);
+    pack_mask_kernel<<<grid, 32, 0, st>>>(V);
+    CU(cudaGetLastError());
     return PQB_OK;
 }
 
@@ -368,8 +446,7 @@ extern "C" int pqb_panel_upload(pqb_panel *p) {
         }
         if ((rc = launch_conv(p, true, rm, tl, n, s0, ns, st))) return rc;
     }
-    CU(cudaMemcpyAsync(p->d_start, p->h_start.data(), (size_t)p->n_symbols * sizeof(int), cudaMemcpyHostToDevice, st));
-    return PQB_OK;
+    return prepare_nulls(p, st);
 }
 
 // tiled device planes -> pinned row-major staging (outputs + validity, or the input fields)
@@ -465,7 +542,10 @@ static int build_args(const pqb_panel *p, const pqb_suite_params *sp, Built *out
 
     for (int f = 0; f < PQB_N_FIELDS; ++f) A.in[f] = p->d_in[f];
     for (int k = 0; k < PQB_N_OUTPUTS; ++k) { A.out[k] = nullptr; out->lead[k] = NEVER; }
-    A.start = p->starts_nonzero ? p->d_start : nullptr;
+    A.start = (p->starts_nonzero && !p->nulls_mode) ? p->d_start : nullptr;
+    A.vmask = p->nulls_mode ? p->d_vmask : nullptr;
+    A.symflags = p->nulls_mode ? p->d_flags : nullptr;
+    for (int k = 0; k < PQB_N_OUTPUTS; ++k) A.ovm[k] = p->nulls_mode ? p->d_ovm[k] : nullptr;
     A.n_symbols = (int)p->n_symbols;
     A.n_bars = n_bars;
     A.n_blocks = (int)p->n_blocks;
@@ -671,8 +751,9 @@ static int launch_suite(pqb_panel *p, const Built &full, int64_t b0, int64_t nb,
 #endif
         bool fulls = a.gmask == G_ALL;
         for (int k = 0; k < PQB_N_OUTPUTS; ++k) fulls &= a.out[k] != nullptr;
-        if (fulls) suite_fused_kernel<true><<<(unsigned)nb, CTA_THREADS, a.smem_bytes, e->stream>>>(a);
-        else suite_fused_kernel<false><<<(unsigned)nb, CTA_THREADS, a.smem_bytes, e->stream>>>(a);
+        if (a.vmask) suite_fused_kernel<false, true><<<(unsigned)nb, CTA_THREADS, a.smem_bytes, e->stream>>>(a);
+        else if (fulls) suite_fused_kernel<true, false><<<(unsigned)nb, CTA_THREADS, a.smem_bytes, e->stream>>>(a);
+        else suite_fused_kernel<false, false><<<(unsigned)nb, CTA_THREADS, a.smem_bytes, e->stream>>>(a);
         CU(cudaGetLastError());
         ++n_launch;
     }
@@ -688,6 +769,32 @@ static int launch_suite(pqb_panel *p, const Built &full, int64_t b0, int64_t nb,
 #endif
     if (ev_after_fused) CU(cudaEventRecord(ev_after_fused, e->stream));
     const int64_t s0 = b0 * SYM, ns = std::min<int64_t>(nb * SYM, p->n_symbols - s0);
+    if (p->nulls_mode) {
+        // the kernel wrote per-bar validity words; turn them into the Arrow bitmaps of these symbols
+        MaskArgs M{};
+        int n = 0;
+        for (int k = 0; k < PQB_N_OUTPUTS; ++k) {
+            if (!(full.a.out[k] && p->d_bits[k])) continue;
+            if (stored >> k & 1) {
+                M.tiled_in[n] = p->d_ovm[k] + (size_t)b0 * p->bars_padded;
+                M.rm_out[n] = p->d_bits[k] + (size_t)s0 * p->words_per_row;
+                ++n;
+            } else {
+                CU(cudaMemsetAsync(p->d_bits[k] + (size_t)s0 * p->words_per_row, 0,
+                                   (size_t)ns * p->words_per_row * sizeof(uint32_t), e->stream));
+            }
+        }
+        M.n_planes = n; M.n_symbols = (int)ns; M.n_bars = (int)p->n_bars; M.bars_padded = (int)p->bars_padded;
+        M.words_per_row = (int)p->words_per_row; M.n_blocks = (int)nb;
+        if (n) {
+            dim3 grid((unsigned)p->words_per_row, (unsigned)nb);
+            unpack_mask_kernel<<<grid, 32, 0, e->stream>>>(M);
+            CU(cudaGetLastError());
+            ++n_launch;
+        }
+        if (launches) *launches = n_launch;
+        return PQB_OK;
+    }
     ValidityArgs V{};
     bool any = false;
     for (int k = 0; k < PQB_N_OUTPUTS; ++k) {
@@ -747,7 +854,8 @@ extern "C" int pqb_suite_run_host(pqb_panel *p, const pqb_suite_params *sp, int6
     std::vector<cudaEvent_t> up((size_t)n_chunks), done((size_t)n_chunks);
     for (auto &x : up) CU(cudaEventCreateWithFlags(&x, cudaEventDisableTiming));
     for (auto &x : done) CU(cudaEventCreateWithFlags(&x, cudaEventDisableTiming));
-    CU(cudaMemcpyAsync(p->d_start, p->h_start.data(), (size_t)p->n_symbols * sizeof(int), cudaMemcpyHostToDevice, e->h2d));
+    if ((rc = prepare_nulls(p, e->h2d))) return rc;
+    if ((rc = build_args(p, sp, &full))) return rc;      // (mode may have changed)
     int total_launches = 0;
     for (int64_t c = 0; c < n_chunks; ++c) {
         const int b = (int)(c & 1);
@@ -973,17 +1081,10 @@ static int run_single(pqb_engine *e, const pqb_col *const *cols, const int *fiel
     const int64_t n = cols[0]->len;
     for (int i = 1; i < n_cols; ++i)
         if (cols[i]->len != n) return fail(PQB_ERR_INVALID, "input columns differ in length");
-    int64_t lead = -1;
     for (int i = 0; i < n_cols; ++i) {
         ColCheck cc = scan_col(cols[i]);
         if (cc.any_null && np == NP_ERR)
             return fail(PQB_ERR_NULLS, "chunked array is not contiguous (input %d has nulls; reference: cont_slice()?)", i);
-        if (cc.interior)
-            return fail(PQB_ERR_UNSUPPORTED, "input %d has nulls after its first valid value (not built)", i);
-        if (lead >= 0 && cc.lead != lead)
-            return fail(PQB_ERR_UNSUPPORTED, "inputs start at different rows (%lld vs %lld; not built)", (long long)lead,
-                        (long long)cc.lead);
-        lead = cc.lead;
     }
     if (n == 0) return PQB_OK;
     // device required from here on
@@ -999,7 +1100,11 @@ static int run_single(pqb_engine *e, const pqb_col *const *cols, const int *fiel
     pqb_panel *p = e->scratch;
     for (int f = 0; f < PQB_N_FIELDS; ++f) memset(p->h_in[f], 0, (size_t)p->pitch * sizeof(double));
     p->h_start[0] = 0;
+    p->h_start_explicit[0] = 0;
     p->starts_nonzero = false;
+    p->has_interior = false;
+    p->h_flags[0] = 0;
+    for (int f = 0; f < PQB_N_FIELDS; ++f) { p->h_lead[f][0] = -1; p->h_vin[f].clear(); }
     for (int i = 0; i < n_cols; ++i)
         if ((rc = pqb_panel_set_column(p, 0, fields[i], cols[i]->values, cols[i]->validity, cols[i]->offset, n))) return rc;
     if ((rc = pqb_panel_upload(p))) return rc;

@@ -1,0 +1,172 @@
+"""Null-aware mode of the CUDA path (interior / trailing nulls, fields starting at different rows)
+against the oracle's null semantics, function by function, bit-exact (SURVEY.md 8a conventions:
+overlap/volatility/volume functions skip nulls, trange/obv use a positional shift, STOCH uses polars'
+positional rolling windows, momentum.rs functions and midprice fail -> all-null column)."""
+import numpy as np
+import pytest
+
+import synth
+from oracle import pqo
+
+pytestmark = pytest.mark.gpu
+
+import tolerances as T
+
+F = ("close", "high", "low", "volume")
+
+
+def _panel_with_nulls(pq, d, ok):
+    S, N = d["close"].shape
+    panel = pq.Panel(S, N)
+    for s in range(S):
+        for f in F:
+            bits = np.packbits(ok[f][s].astype(np.uint8), bitorder="little")
+            panel.set_column(s, f, d[f][s], validity=bits)
+    return panel
+
+
+def _check(name, res, s, ref):
+    v, k = ref
+    nbad, msg = T.compare(name, res[name][0][s], res[name][1][s], v, k)
+    assert nbad == 0, f"symbol {s}: {msg}"
+
+
+def _null_masks(S, N, seed, frac=0.03):
+    rng = np.random.default_rng(seed)
+    ok = {f: rng.random((S, N)) >= frac for f in F}
+    for f in F:
+        ok[f][0] = True                                      # symbol 0: no nulls at all
+    lead = rng.integers(0, 60, S)
+    for s in range(1, S):
+        for f in F:
+            ok[f][s, :lead[s]] = False                       # shared leading nulls
+    ok["volume"][2, :25] = False                             # a field that starts later than the others
+    for f in F:
+        ok[f][3, N - 40:] = False                            # delisted: trailing nulls
+        ok[f][4] = True
+    ok["close"][4, 100] = False                              # exactly one interior null
+    for f in F:
+        ok[f][5] = True
+        ok[f][5, :17] = False                                # leading nulls only, same for all fields
+    return ok
+
+
+def test_null_semantics_function_by_function(pq=None):
+    import polars_quant_b200 as pq
+    S, N = 40, 700
+    d = synth.ohlcv(S, N, seed=31)
+    ok = _null_masks(S, N, seed=8)
+    panel = _panel_with_nulls(pq, d, ok)
+    res = panel.compute()
+    c, h, l, v = (d[f] for f in F)
+    kc, kh, kl, kv = (ok[f] for f in F)
+    for s in range(S):
+        _check("sma", res, s, pqo.sma(c[s], 30, kc[s]))
+        _check("ema", res, s, pqo.ema(c[s], 30, kc[s]))
+        _check("tema", res, s, pqo.tema(c[s], 30, kc[s]))
+        _check("trima", res, s, pqo.trima(c[s], 30, kc[s]))
+        for name, ref in zip(("bb_upper", "bb_middle", "bb_lower"), pqo.bbands(c[s], 20, 2.0, 2.0, kc[s])):
+            _check(name, res, s, ref)
+        _check("trange", res, s, pqo.trange(h[s], l[s], c[s], kh[s], kl[s], kc[s]))
+        _check("atr", res, s, pqo.atr(h[s], l[s], c[s], 14, kh[s], kl[s], kc[s]))
+        _check("natr", res, s, pqo.natr(h[s], l[s], c[s], 14, kh[s], kl[s], kc[s]))
+        _check("obv", res, s, pqo.obv(c[s], v[s], kc[s], kv[s]))
+        _check("ad", res, s, pqo.ad(h[s], l[s], c[s], v[s], kh[s], kl[s], kc[s], kv[s]))
+        sk, sd = pqo.stoch(h[s], l[s], c[s], 9, 3, 0, 3, 0, kh[s], kl[s], kc[s])
+        _check("kdj_k", res, s, sk)
+        _check("kdj_d", res, s, sd)
+        jok = sk[1] & sd[1]
+        _check("kdj_j", res, s, (np.where(jok, 3.0 * sk[0] - 2.0 * sd[0], np.nan), jok))
+        # momentum.rs functions / midprice: the reference fails on interior or trailing nulls
+        lead_only = {f: (not ok[f][s].all()) and ok[f][s][np.argmax(ok[f][s]):].all() for f in F}
+        clean = {f: ok[f][s].all() or lead_only[f] for f in F}
+        a = int(np.argmax(kc[s]))
+        if clean["close"]:
+            for name, ref in zip(("macd", "macd_signal", "macd_hist"), pqo.macd(c[s, a:], 12, 26, 9)):
+                full_v = np.full(N, np.nan); full_k = np.zeros(N, bool)
+                full_v[a:], full_k[a:] = ref
+                _check(name, res, s, (full_v, full_k))
+            rv, rk = pqo.rsi(c[s, a:], 14)
+            full_v = np.full(N, np.nan); full_k = np.zeros(N, bool); full_v[a:], full_k[a:] = rv, rk
+            _check("rsi", res, s, (full_v, full_k))
+        else:
+            for name in ("macd", "macd_signal", "macd_hist", "rsi"):
+                assert not res[name][1][s].any(), f"{name} symbol {s}: reference fails on nulls -> all null"
+        if not (clean["close"] and clean["high"] and clean["low"]):
+            assert not res["willr"][1][s].any()
+        if not (clean["high"] and clean["low"]):
+            assert not res["midprice"][1][s].any()
+    # symbols without interior nulls and with one common start are exactly the trimmed series
+    for s in (0, 5):
+        a = int(np.argmax(kc[s]))
+        out, okk, _ = pqo.suite_panel(c[s:s + 1, a:], h[s:s + 1, a:], l[s:s + 1, a:], v[s:s + 1, a:])
+        for j, name in enumerate(pqo.OUTPUT_NAMES):
+            full_v = np.full(N, np.nan); full_k = np.zeros(N, bool)
+            full_v[a:], full_k[a:] = out[j, 0], okk[j, 0]
+            _check(name, res, s, (full_v, full_k))
+    panel.close()
+
+
+def test_null_mode_host_pipeline_and_plain_mode_agree():
+    """A panel whose only nulls are shared leading nulls gives the same bytes whether it runs in the
+    plain mode (starts) or is forced through the null-aware kernel by one extra interior null in a
+    different symbol; run_host == compute in null-aware mode."""
+    import polars_quant_b200 as pq
+    S, N = 70, 400
+    d = synth.ohlcv(S, N, seed=13)
+    ok = {f: np.ones((S, N), bool) for f in F}
+    for f in F:
+        ok[f][7, :33] = False
+    plain = _panel_with_nulls(pq, d, ok)
+    r_plain = {k: (a.copy(), b.copy()) for k, (a, b) in plain.compute().items()}
+    ok["close"][50, 200] = False
+    nul = _panel_with_nulls(pq, d, ok)
+    r_null = {k: (a.copy(), b.copy()) for k, (a, b) in nul.compute().items()}
+    for name in r_plain:
+        for s in list(range(0, 50)) + list(range(51, S)):
+            assert np.array_equal(r_plain[name][1][s], r_null[name][1][s]), (name, s)
+            assert T.same_bits(r_plain[name][0][s], r_null[name][0][s]).all(), (name, s)
+    nul.run_host(chunk_symbols=32)
+    r_host = nul.outputs()
+    for name in r_null:
+        assert np.array_equal(r_null[name][1], r_host[name][1]), name
+        assert T.same_bits(r_null[name][0], r_host[name][0]).all(), name
+    plain.close(); nul.close()
+
+
+def test_single_column_calls_with_nulls():
+    """pqb_sma / pqb_ema / pqb_atr / pqb_obv skip nulls like the reference; pqb_rsi / pqb_macd refuse."""
+    import ctypes as C
+    import polars_quant_b200 as pq
+    from polars_quant_b200 import _native as N
+    L = N.lib()
+    eng = pq.get_engine(0)
+    n = 500
+    d = synth.ohlcv(1, n, seed=99)
+    rng = np.random.default_rng(3)
+    ok = rng.random(n) > 0.05
+    bits = np.packbits(ok.astype(np.uint8), bitorder="little")
+    c = np.ascontiguousarray(d["close"][0]); h = np.ascontiguousarray(d["high"][0]); l = np.ascontiguousarray(d["low"][0])
+    v = np.ascontiguousarray(d["volume"][0])
+    col = lambda a, b=None: N.Col(a.ctypes.data, None if b is None else b.ctypes.data, 0, n)
+    out_v, out_b = np.empty(n), np.zeros((n + 7) // 8, np.uint8)
+    oc = N.OutCol(out_v.ctypes.data, out_b.ctypes.data)
+
+    def got():
+        return out_v.copy(), np.unpackbits(out_b, bitorder="little")[:n].astype(bool)
+
+    cc = col(c, bits)
+    N.check(L.pqb_sma(eng._h, C.byref(cc), 10, C.byref(oc)))
+    assert T.compare("sma", *got(), *pqo.sma(c, 10, ok))[0] == 0
+    N.check(L.pqb_ema(eng._h, C.byref(cc), 10, C.byref(oc)))
+    assert T.compare("ema", *got(), *pqo.ema(c, 10, ok))[0] == 0
+    ch, cl = col(h), col(l)
+    N.check(L.pqb_atr(eng._h, C.byref(ch), C.byref(cl), C.byref(cc), 14, C.byref(oc)))
+    assert T.compare("atr", *got(), *pqo.atr(h, l, c, 14, None, None, ok))[0] == 0
+    cv = col(v)
+    N.check(L.pqb_obv(eng._h, C.byref(cc), C.byref(cv), C.byref(oc)))
+    assert T.compare("obv", *got(), *pqo.obv(c, v, ok, None))[0] == 0
+    assert L.pqb_rsi(eng._h, C.byref(cc), 14, C.byref(oc)) == -5
+    # and a clean call right after a null-aware one (scratch panel state is reset)
+    N.check(L.pqb_sma(eng._h, C.byref(col(c)), 10, C.byref(oc)))
+    assert T.compare("sma", *got(), *pqo.sma(c, 10))[0] == 0
