@@ -68,6 +68,8 @@ extern "C" void pqb_suite_params_default(pqb_suite_params *p) {
     p->rsi_period = 14; p->atr_period = 14; p->natr_period = 14;
     p->kdj_fastk = 9; p->kdj_slowk = 3; p->kdj_slowd = 3;
     p->willr_period = 14; p->midprice_period = 14;
+    p->midpoint_period = 14; p->adosc_fast = 3; p->adosc_slow = 10; p->mom_period = 10; p->roc_period = 10;
+    p->cmo_period = 14; p->mfi_period = 14; p->cci_period = 14;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -525,7 +527,7 @@ static int build_args(const pqb_panel *p, const pqb_suite_params *sp, Built *out
     memset(out, 0, sizeof *out);
     const int n_bars = (int)p->n_bars;
     const int NEVER = n_bars;                       // lead that makes a column all-null
-    uint32_t ind = sp->indicators & PQB_IND_ALL;
+    uint32_t ind = sp->indicators & (PQB_IND_ALL | PQB_IND_EXTRAS);
     auto need_fields = [&](uint32_t mask, const char *what) -> int {
         if ((p->fields_mask & mask) != mask) return fail(PQB_ERR_INVALID, "%s needs panel fields 0x%x", what, mask);
         return PQB_OK;
@@ -538,14 +540,20 @@ static int build_args(const pqb_panel *p, const pqb_suite_params *sp, Built *out
         (rc = need_fields(C | H | L, "high/low/close indicators"))) return rc;
     if ((ind & PQB_IND_MIDPRICE) && (rc = need_fields(H | L, "midprice"))) return rc;
     if ((ind & PQB_IND_OBV) && (rc = need_fields(C | V, "obv"))) return rc;
-    if ((ind & PQB_IND_AD) && (rc = need_fields(C | H | L | V, "ad"))) return rc;
+    if ((ind & (PQB_IND_AD | PQB_IND_ADOSC | PQB_IND_MFI)) && (rc = need_fields(C | H | L | V, "ad / adosc / mfi"))) return rc;
+    if ((ind & (PQB_IND_MIDPOINT | PQB_IND_MOM | PQB_IND_ROC | PQB_IND_CMO)) && (rc = need_fields(C, "close-based indicators"))) return rc;
+    if ((ind & PQB_IND_CCI) && (rc = need_fields(C | H | L, "cci"))) return rc;
+    if ((ind & PQB_IND_EXTRAS) && p->nulls_mode)
+        return fail(PQB_ERR_UNSUPPORTED, "midpoint / adosc / mom / roc / cmo / mfi / cci are not built for panels with "
+                                         "interior nulls yet (momentum.rs functions fail on such input in the reference)");
 
     for (int f = 0; f < PQB_N_FIELDS; ++f) A.in[f] = p->d_in[f];
     for (int k = 0; k < PQB_N_OUTPUTS; ++k) { A.out[k] = nullptr; out->lead[k] = NEVER; }
     A.start = (p->starts_nonzero && !p->nulls_mode) ? p->d_start : nullptr;
     A.vmask = p->nulls_mode ? p->d_vmask : nullptr;
     A.symflags = p->nulls_mode ? p->d_flags : nullptr;
-    for (int k = 0; k < PQB_N_OUTPUTS; ++k) A.ovm[k] = p->nulls_mode ? p->d_ovm[k] : nullptr;
+    // validity words: every output in the null-aware mode; the optional groups always (roc / cci decide per bar)
+    for (int k = 0; k < PQB_N_OUTPUTS; ++k) A.ovm[k] = (p->nulls_mode || k >= PQB_N_SUITE_OUTPUTS) ? p->d_ovm[k] : nullptr;
     A.n_symbols = (int)p->n_symbols;
     A.n_bars = n_bars;
     A.n_blocks = (int)p->n_blocks;
@@ -660,15 +668,51 @@ static int build_args(const pqb_panel *p, const pqb_suite_params *sp, Built *out
             return fail(PQB_ERR_UNSUPPORTED, "midprice period %d (reference: never-expiring deque) is not built", sp->midprice_period);
         A.gmask |= G_MIDPRICE; A.mid_p = sp->midprice_period; bind(PQB_OUT_MIDPRICE, 0);
     }
+    // ---- optional groups (not part of the benchmark suite) ----
+    auto bind_dyn = [&](int k) { if (want(k)) { A.out[k] = p->d_out[k]; out->lead[k] = NEVER; } };   // validity from the kernel
+    if (ind & PQB_IND_MIDPOINT) {
+        if (sp->midpoint_period <= 0) return fail(PQB_ERR_UNSUPPORTED, "midpoint period %d (reference: never-expiring deque) is not built", sp->midpoint_period);
+        A.gmask |= G_MIDPOINT; A.midpoint_p = sp->midpoint_period; bind_dyn(PQB_OUT_MIDPOINT);
+    }
+    if (ind & PQB_IND_ADOSC) {
+        const int f = sp->adosc_fast, sl = sp->adosc_slow;
+        if (f <= 0 || sl <= 0) return fail(PQB_ERR_UNSUPPORTED, "adosc with a period <= 0 is not built");
+        A.gmask |= G_ADOSC; A.adosc_f = f; A.adosc_s = sl; A.a_adf = ema_alpha(f); A.a_ads = ema_alpha(sl);
+        bind_dyn(PQB_OUT_ADOSC); upto(std::max(f, sl));
+    }
+    if (ind & PQB_IND_MOM) {
+        if (sp->mom_period <= 0) return fail(PQB_ERR_UNSUPPORTED, "mom period %d <= 0 is not built", sp->mom_period);
+        A.gmask |= G_MOM; A.mom_p = sp->mom_period; bind_dyn(PQB_OUT_MOM); upto(sp->mom_period);
+    }
+    if (ind & PQB_IND_ROC) {
+        if (sp->roc_period <= 0) return fail(PQB_ERR_UNSUPPORTED, "roc period %d <= 0 is not built", sp->roc_period);
+        A.gmask |= G_ROC; A.roc_p = sp->roc_period; upto(sp->roc_period);
+        for (int k = PQB_OUT_ROC; k <= PQB_OUT_ROCR100; ++k) bind_dyn(k);
+    }
+    if (ind & PQB_IND_CMO) {
+        if (sp->cmo_period <= 0) { null_only(PQB_OUT_CMO); }                 // momentum.rs: nothing emitted
+        else { A.gmask |= G_CMO; A.cmo_p = sp->cmo_period; bind_dyn(PQB_OUT_CMO); upto(sp->cmo_period); }
+    }
+    if (ind & PQB_IND_MFI) {
+        if (sp->mfi_period <= 0) return fail(PQB_ERR_UNSUPPORTED, "mfi period %d <= 0 is not built", sp->mfi_period);
+        A.gmask |= G_MFI; A.mfi_p = sp->mfi_period; bind_dyn(PQB_OUT_MFI); upto((long long)sp->mfi_period + 1);
+    }
+    if (ind & PQB_IND_CCI) {
+        if (sp->cci_period <= 0) { null_only(PQB_OUT_CCI); }                 // calc_sma guard: all null
+        else { A.gmask |= G_CCI; A.cci_p = sp->cci_period; A.cci_pd = (double)sp->cci_period; A.inv_cci = 1.0 / (double)sp->cci_period;
+               bind_dyn(PQB_OUT_CCI); upto(sp->cci_period); }
+    }
+    for (int k = PQB_N_SUITE_OUTPUTS; k < PQB_N_OUTPUTS; ++k)
+        if (A.out[k] && !p->d_ovm[k]) return fail(PQB_ERR_INVALID, "internal: validity words of output %d are not allocated", k);
     A.steady_lead = steady;
 
     // roles with work, planes to stage
     A.roles = 0; A.n_roles = 0; A.fields = 0;
     for (int r = 0; r < N_ROLES; ++r)
         if (A.gmask & ROLE_GROUPS[r]) { A.roles |= 1u << r; ++A.n_roles; }
-    if (A.gmask & (G_SMA | G_EMA | G_TEMA | G_TRIMA | G_BB | G_MACD | G_RSI | G_TRANGE | G_ATR | G_NATR | G_OBV | G_AD | G_KDJ | G_WILLR)) A.fields |= F_C;
-    if (A.gmask & (G_TRANGE | G_ATR | G_NATR | G_AD | G_KDJ | G_WILLR | G_MIDPRICE)) A.fields |= F_H | F_L;
-    if (A.gmask & (G_OBV | G_AD)) A.fields |= F_V;
+    if (A.gmask & ~(unsigned)G_MIDPRICE) A.fields |= F_C;                     // everything but midprice reads close
+    if (A.gmask & (G_TRANGE | G_ATR | G_NATR | G_AD | G_KDJ | G_WILLR | G_MIDPRICE | G_ADOSC | G_MFI | G_CCI)) A.fields |= F_H | F_L;
+    if (A.gmask & (G_OBV | G_AD | G_ADOSC | G_MFI)) A.fields |= F_V;
 
     // shared-memory rings (slots of 32 doubles)
     long long off = 0;
@@ -686,6 +730,12 @@ static int build_args(const pqb_panel *p, const pqb_suite_params *sp, Built *out
     A.off_wh = take(wp); A.off_wl = take(wp);
     A.off_mh = take(mp); A.off_ml = take(mp);
     A.off_kh = take(kp); A.off_kl = take(kp);
+    A.off_mom = take((A.gmask & G_MOM) ? A.mom_p : 0);
+    A.off_roc = take((A.gmask & G_ROC) ? A.roc_p : 0);
+    A.off_cmou = take((A.gmask & G_CMO) ? A.cmo_p : 0); A.off_cmod = take((A.gmask & G_CMO) ? A.cmo_p : 0);
+    A.off_mfip = take((A.gmask & G_MFI) ? A.mfi_p : 0); A.off_mfin = take((A.gmask & G_MFI) ? A.mfi_p : 0);
+    A.off_cci = take((A.gmask & G_CCI) ? A.cci_p : 0);
+    A.off_mph = take((A.gmask & G_MIDPOINT) ? A.midpoint_p + 1 : 0); A.off_mpl = take((A.gmask & G_MIDPOINT) ? A.midpoint_p + 1 : 0);
     const long long smem = (long long)kFixedSmem + off * 8;
     if (smem > kMaxSmem)
         return fail(PQB_ERR_UNSUPPORTED,
@@ -723,6 +773,13 @@ static uint32_t outputs_of_groups(unsigned g) {
     if (g & G_KDJ) m |= 7u << 16;
     if (g & G_WILLR) m |= 1u << 19;
     if (g & G_MIDPRICE) m |= 1u << 20;
+    if (g & G_MIDPOINT) m |= 1u << 21;
+    if (g & G_ADOSC) m |= 1u << 22;
+    if (g & G_MOM) m |= 1u << 23;
+    if (g & G_ROC) m |= 0xfu << 24;
+    if (g & G_CMO) m |= 1u << 28;
+    if (g & G_MFI) m |= 1u << 29;
+    if (g & G_CCI) m |= 1u << 30;
     return m;
 }
 
@@ -749,8 +806,8 @@ static int launch_suite(pqb_panel *p, const Built &full, int64_t b0, int64_t nb,
 #else
         a.dbg = nullptr;
 #endif
-        bool fulls = a.gmask == G_ALL;
-        for (int k = 0; k < PQB_N_OUTPUTS; ++k) fulls &= a.out[k] != nullptr;
+        bool fulls = a.gmask == G_ALL;                                       // exactly the benchmark suite
+        for (int k = 0; k < PQB_N_SUITE_OUTPUTS; ++k) fulls &= a.out[k] != nullptr;
         if (a.vmask) suite_fused_kernel<false, true><<<(unsigned)nb, CTA_THREADS, a.smem_bytes, e->stream>>>(a);
         else if (fulls) suite_fused_kernel<true, false><<<(unsigned)nb, CTA_THREADS, a.smem_bytes, e->stream>>>(a);
         else suite_fused_kernel<false, false><<<(unsigned)nb, CTA_THREADS, a.smem_bytes, e->stream>>>(a);
@@ -795,10 +852,33 @@ static int launch_suite(pqb_panel *p, const Built &full, int64_t b0, int64_t nb,
         if (launches) *launches = n_launch;
         return PQB_OK;
     }
+    {   // optional groups: validity words written by the kernel (or all-null for a period-0 column)
+        MaskArgs M{};
+        int n = 0;
+        for (int k = PQB_N_SUITE_OUTPUTS; k < PQB_N_OUTPUTS; ++k) {
+            if (!(full.a.out[k] && p->d_bits[k])) continue;
+            if (stored >> k & 1) {
+                M.tiled_in[n] = p->d_ovm[k] + (size_t)b0 * p->bars_padded;
+                M.rm_out[n] = p->d_bits[k] + (size_t)s0 * p->words_per_row;
+                ++n;
+            } else {
+                CU(cudaMemsetAsync(p->d_bits[k] + (size_t)s0 * p->words_per_row, 0,
+                                   (size_t)ns * p->words_per_row * sizeof(uint32_t), e->stream));
+            }
+        }
+        if (n) {
+            M.n_planes = n; M.n_symbols = (int)ns; M.n_bars = (int)p->n_bars; M.bars_padded = (int)p->bars_padded;
+            M.words_per_row = (int)p->words_per_row; M.n_blocks = (int)nb;
+            dim3 grid((unsigned)p->words_per_row, (unsigned)nb);
+            unpack_mask_kernel<<<grid, 32, 0, e->stream>>>(M);
+            CU(cudaGetLastError());
+            ++n_launch;
+        }
+    }
     ValidityArgs V{};
     bool any = false;
     for (int k = 0; k < PQB_N_OUTPUTS; ++k) {
-        V.bits[k] = (full.a.out[k] && p->d_bits[k]) ? p->d_bits[k] + (size_t)s0 * p->words_per_row : nullptr;
+        V.bits[k] = (k < PQB_N_SUITE_OUTPUTS && full.a.out[k] && p->d_bits[k]) ? p->d_bits[k] + (size_t)s0 * p->words_per_row : nullptr;
         V.lead[k] = full.lead[k];
         any |= V.bits[k] != nullptr;
     }
@@ -817,10 +897,20 @@ static int launch_suite(pqb_panel *p, const Built &full, int64_t b0, int64_t nb,
     return PQB_OK;
 }
 
+// the optional groups report validity per bar: allocate their validity-word planes on first use
+static int ensure_extra_masks(pqb_panel *p, const pqb_suite_params *sp) {
+    if (!(sp->indicators & PQB_IND_EXTRAS)) return PQB_OK;
+    const size_t mwords = (size_t)p->n_blocks * p->bars_padded;
+    for (int k = PQB_N_SUITE_OUTPUTS; k < PQB_N_OUTPUTS; ++k)
+        if (p->d_out[k] && !p->d_ovm[k]) CU(cudaMalloc(&p->d_ovm[k], mwords * sizeof(uint32_t)));
+    return PQB_OK;
+}
+
 static int run_suite(pqb_panel *p, const pqb_suite_params *sp, cudaEvent_t ev_after_fused, int *launches) {
     if (!p || !sp) return fail(PQB_ERR_INVALID, "pqb_suite_run: NULL argument");
     int rc = set_dev(p->e);
     if (rc) return rc;
+    if ((rc = ensure_extra_masks(p, sp))) return rc;
     Built b;
     if ((rc = build_args(p, sp, &b))) return rc;
     int nl = 0;
@@ -846,6 +936,7 @@ extern "C" int pqb_suite_run_host(pqb_panel *p, const pqb_suite_params *sp, int6
     if (rc) return rc;
     pqb_engine *e = p->e;
     Built full;
+    if ((rc = ensure_extra_masks(p, sp))) return rc;
     if ((rc = build_args(p, sp, &full))) return rc;
     if (chunk_symbols <= 0 || chunk_symbols > p->chunk_symbols) chunk_symbols = p->chunk_symbols;
     chunk_symbols = std::max<int64_t>(SYM, chunk_symbols / SYM * SYM);
@@ -1229,4 +1320,47 @@ extern "C" int pqb_midprice(pqb_engine *e, const pqb_col *h, const pqb_col *l, i
     // nulls in `low` make the reference fail (overlap.rs:352-376); nulls in `high` alone would
     // need a per-field start: both are refused.
     return run_single(e, c, f, 2, NP_ERR, &sp, o, d, 1);
+}
+
+// ---- the remaining SURVEY.md 8a functions ----
+extern "C" int pqb_midpoint(pqb_engine *e, const pqb_col *real, int32_t tp, pqb_out_col *out) {
+    pqb_suite_params sp = only(PQB_IND_MIDPOINT); sp.midpoint_period = tp;
+    const pqb_col *c[] = {real}; const int f[] = {PQB_CLOSE}; const int o[] = {PQB_OUT_MIDPOINT}; pqb_out_col *d[] = {out};
+    return run_single(e, c, f, 1, NP_ERR, &sp, o, d, 1);      // (null-skipping in the reference; not built with nulls yet)
+}
+extern "C" int pqb_adosc(pqb_engine *e, const pqb_col *h, const pqb_col *l, const pqb_col *cl, const pqb_col *v,
+                         int32_t fp, int32_t slp, pqb_out_col *out) {
+    pqb_suite_params sp = only(PQB_IND_ADOSC); sp.adosc_fast = fp; sp.adosc_slow = slp;
+    const pqb_col *c[] = {h, l, cl, v}; const int f[] = {PQB_HIGH, PQB_LOW, PQB_CLOSE, PQB_VOLUME};
+    const int o[] = {PQB_OUT_ADOSC}; pqb_out_col *d[] = {out};
+    return run_single(e, c, f, 4, NP_ERR, &sp, o, d, 1);
+}
+extern "C" int pqb_mom(pqb_engine *e, const pqb_col *real, int32_t tp, pqb_out_col *out) {
+    pqb_suite_params sp = only(PQB_IND_MOM); sp.mom_period = tp;
+    const pqb_col *c[] = {real}; const int f[] = {PQB_CLOSE}; const int o[] = {PQB_OUT_MOM}; pqb_out_col *d[] = {out};
+    return run_single(e, c, f, 1, NP_ERR, &sp, o, d, 1);
+}
+extern "C" int pqb_roc(pqb_engine *e, const pqb_col *real, int32_t tp, int32_t kind, pqb_out_col *out) {
+    if (kind < 0 || kind > 3) return fail(PQB_ERR_INVALID, "pqb_roc: kind %d not in 0..3", kind);
+    pqb_suite_params sp = only(PQB_IND_ROC); sp.roc_period = tp;
+    const pqb_col *c[] = {real}; const int f[] = {PQB_CLOSE}; const int o[] = {PQB_OUT_ROC + kind}; pqb_out_col *d[] = {out};
+    return run_single(e, c, f, 1, NP_ERR, &sp, o, d, 1);
+}
+extern "C" int pqb_cmo(pqb_engine *e, const pqb_col *real, int32_t tp, pqb_out_col *out) {
+    pqb_suite_params sp = only(PQB_IND_CMO); sp.cmo_period = tp;
+    const pqb_col *c[] = {real}; const int f[] = {PQB_CLOSE}; const int o[] = {PQB_OUT_CMO}; pqb_out_col *d[] = {out};
+    return run_single(e, c, f, 1, NP_ERR, &sp, o, d, 1);
+}
+extern "C" int pqb_mfi(pqb_engine *e, const pqb_col *h, const pqb_col *l, const pqb_col *cl, const pqb_col *v, int32_t tp,
+                       pqb_out_col *out) {
+    pqb_suite_params sp = only(PQB_IND_MFI); sp.mfi_period = tp;
+    const pqb_col *c[] = {h, l, cl, v}; const int f[] = {PQB_HIGH, PQB_LOW, PQB_CLOSE, PQB_VOLUME};
+    const int o[] = {PQB_OUT_MFI}; pqb_out_col *d[] = {out};
+    return run_single(e, c, f, 4, NP_ERR, &sp, o, d, 1);
+}
+extern "C" int pqb_cci(pqb_engine *e, const pqb_col *h, const pqb_col *l, const pqb_col *cl, int32_t tp, pqb_out_col *out) {
+    pqb_suite_params sp = only(PQB_IND_CCI); sp.cci_period = tp;
+    const pqb_col *c[] = {h, l, cl}; const int f[] = {PQB_HIGH, PQB_LOW, PQB_CLOSE}; const int o[] = {PQB_OUT_CCI};
+    pqb_out_col *d[] = {out};
+    return run_single(e, c, f, 3, NP_ERR, &sp, o, d, 1);
 }

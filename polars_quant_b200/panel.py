@@ -47,7 +47,7 @@ class Panel:
     FIELDS = {"close": N.CLOSE, "high": N.HIGH, "low": N.LOW, "volume": N.VOLUME}
 
     def __init__(self, n_symbols: int, n_bars: int, engine: Engine | None = None, fields_mask: int = 0xF,
-                 outputs_mask: int = (1 << N.N_OUTPUTS) - 1, host_staging: bool = True):
+                 outputs_mask: int = (1 << N.N_SUITE_OUTPUTS) - 1, host_staging: bool = True):
         self.engine = engine or get_engine(0)
         self.n_symbols, self.n_bars = int(n_symbols), int(n_bars)
         self.outputs_mask = outputs_mask

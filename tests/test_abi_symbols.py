@@ -27,7 +27,8 @@ def test_header_declares_the_expected_surface():
     for must in ("pqb_engine_create", "pqb_panel_create", "pqb_panel_set_column", "pqb_suite_run",
                  "pqb_suite_run_host", "pqb_panel_get_output", "pqb_sma", "pqb_ema", "pqb_tema", "pqb_trima",
                  "pqb_ma", "pqb_bbands", "pqb_macd", "pqb_rsi", "pqb_trange", "pqb_atr", "pqb_natr", "pqb_obv",
-                 "pqb_ad", "pqb_stoch", "pqb_kdj", "pqb_willr", "pqb_midprice", "pqb_last_error"):
+                 "pqb_ad", "pqb_stoch", "pqb_kdj", "pqb_willr", "pqb_midprice", "pqb_midpoint", "pqb_adosc", "pqb_mom",
+                 "pqb_roc", "pqb_cmo", "pqb_mfi", "pqb_cci", "pqb_last_error"):
         assert must in names
     assert len(names) >= 40
 
@@ -41,7 +42,7 @@ def test_no_cpu_fallback_without_a_device(lib):
     import torch
     if torch.cuda.is_available():
         pytest.skip("a GPU is present")
-    assert lib.pqb_abi_version() == 1
+    assert lib.pqb_abi_version() == 2
     assert lib.pqb_device_count() == 0
     h = C.c_void_p()
     rc = lib.pqb_engine_create(0, C.byref(h))
@@ -58,6 +59,8 @@ def test_default_params_are_the_reference_python_defaults(lib):
     assert (p.atr_period, p.natr_period, p.willr_period, p.midprice_period) == (14, 14, 14, 14)
     assert (p.kdj_fastk, p.kdj_slowk, p.kdj_slowd) == (9, 3, 3)
     assert p.indicators == N.IND_ALL
+    assert (p.midpoint_period, p.adosc_fast, p.adosc_slow, p.mom_period, p.roc_period) == (14, 3, 10, 10, 10)
+    assert (p.cmo_period, p.mfi_period, p.cci_period) == (14, 14, 14)
 
 
 def test_product_never_imports_the_oracle():

@@ -1,0 +1,129 @@
+"""The remaining SURVEY.md 8a functions (optional indicator groups, outputs 21..30): midpoint, adosc,
+mom, roc / rocp / rocr / rocr100, cmo, mfi, cci -- bit-exact against the oracle, including the
+data-dependent nulls of the roc family (lagged value == 0) and cci (mean deviation == 0)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import synth
+from oracle import pqo
+
+pytestmark = pytest.mark.gpu
+
+import tolerances as T
+
+EXTRA_OUT = ("midpoint", "adosc", "mom", "roc", "rocp", "rocr", "rocr100", "cmo", "mfi", "cci")
+
+
+def _refs(d, s, P):
+    c, h, l, v = (d[f][s] for f in ("close", "high", "low", "volume"))
+    return {
+        "midpoint": pqo.midpoint(c, P["midpoint_period"]),
+        "adosc": pqo.adosc(h, l, c, v, P["adosc_fast"], P["adosc_slow"]),
+        "mom": pqo.mom(c, P["mom_period"]),
+        "roc": pqo.roc(c, P["roc_period"], 0), "rocp": pqo.roc(c, P["roc_period"], 1),
+        "rocr": pqo.roc(c, P["roc_period"], 2), "rocr100": pqo.roc(c, P["roc_period"], 3),
+        "cmo": pqo.cmo(c, P["cmo_period"]),
+        "mfi": pqo.mfi(h, l, c, v, P["mfi_period"]),
+        "cci": pqo.cci(h, l, c, P["cci_period"]),
+    }
+
+
+def _data():
+    d = synth.ohlcv(37, 650, seed=71)
+    d["close"][5, 100] = 0.0                                  # roc family: null 10 bars later
+    d["close"][6, ::7] = 0.0
+    flat = np.full(650, 42.0)
+    for f in ("close", "high", "low"):
+        d[f][7] = flat                                        # cci: mean deviation 0 -> null; cmo total 0; mfi neg 0
+    d["volume"][8, 200:260] = 0.0
+    return d
+
+
+@pytest.mark.parametrize("periods", [dict(), dict(midpoint_period=5, adosc_fast=2, adosc_slow=7, mom_period=1, roc_period=3,
+                                                  cmo_period=1, mfi_period=2, cci_period=1),
+                                     dict(midpoint_period=60, adosc_fast=30, adosc_slow=12, mom_period=55, roc_period=41,
+                                          cmo_period=33, mfi_period=29, cci_period=47)])
+def test_optional_groups_alone_and_with_the_suite(periods):
+    import polars_quant_b200 as pq
+    from polars_quant_b200 import _native as N
+    P = dict(midpoint_period=14, adosc_fast=3, adosc_slow=10, mom_period=10, roc_period=10, cmo_period=14,
+             mfi_period=14, cci_period=14)
+    P.update(periods)
+    d = _data()
+    S, NB = d["close"].shape
+    extras = sum(N.IND_EXTRA.values())
+    panel = pq.Panel(S, NB, outputs_mask=(1 << N.N_OUTPUTS) - 1)
+    panel.set_fields(d["close"], d["high"], d["low"], d["volume"])
+    for ind in (extras, extras | N.IND_ALL):
+        res = panel.compute(N.default_params(indicators=ind, **P))
+        for s in range(S):
+            for name, (v, k) in _refs(d, s, P).items():
+                nbad, msg = T.compare(name, res[name][0][s], res[name][1][s], v, k)
+                assert nbad == 0, f"indicators {ind:#x} symbol {s}: {msg}"
+        if ind & N.IND_ALL:                                   # the suite next to them is untouched
+            out, ok, _ = pqo.suite_panel(d["close"], d["high"], d["low"], d["volume"])
+            fails = T.compare_all(res, out, ok, pqo.OUTPUT_NAMES)
+            assert not fails, "\n".join(fails)
+    # one group at a time
+    for g, bit in N.IND_EXTRA.items():
+        res = panel.compute(N.default_params(indicators=bit, **P))
+        names = ("roc", "rocp", "rocr", "rocr100") if g == "roc" else (g,)
+        for s in (0, 5, 6, 7, 8, 36):
+            refs = _refs(d, s, P)
+            for name in names:
+                nbad, msg = T.compare(name, res[name][0][s], res[name][1][s], *refs[name])
+                assert nbad == 0, f"group {g} symbol {s}: {msg}"
+    panel.close()
+
+
+def test_optional_groups_with_leading_nulls_and_host_pipeline():
+    import polars_quant_b200 as pq
+    from polars_quant_b200 import _native as N
+    d = synth.ohlcv(70, 500, seed=12)
+    S, NB = d["close"].shape
+    starts = np.random.default_rng(4).integers(0, 120, S).astype(np.int32)
+    P = dict(midpoint_period=14, adosc_fast=3, adosc_slow=10, mom_period=10, roc_period=10, cmo_period=14,
+             mfi_period=14, cci_period=14)
+    panel = pq.Panel(S, NB, outputs_mask=(1 << N.N_OUTPUTS) - 1)
+    panel.set_fields(d["close"], d["high"], d["low"], d["volume"], starts=starts)
+    panel.run_host(N.default_params(indicators=sum(N.IND_EXTRA.values()) | N.IND_ALL), chunk_symbols=32)
+    res = panel.outputs()
+    for s in range(S):
+        a = int(starts[s])
+        dd = {f: d[f][:, a:] for f in d}
+        for name, (v, k) in _refs(dd, s, P).items():
+            fv = np.full(NB, np.nan); fk = np.zeros(NB, bool)
+            fv[a:], fk[a:] = v, k
+            nbad, msg = T.compare(name, res[name][0][s], res[name][1][s], fv, fk)
+            assert nbad == 0, f"symbol {s} (start {a}): {msg}"
+    panel.close()
+
+
+def test_optional_single_column_entry_points():
+    import polars_quant_b200 as pq
+    from polars_quant_b200 import _native as N
+    L = N.lib()
+    eng = pq.get_engine(0)
+    n = 600
+    d = synth.ohlcv(1, n, seed=123)
+    c, h, l, v = (np.ascontiguousarray(d[f][0]) for f in ("close", "high", "low", "volume"))
+    c[300] = 0.0
+    col = lambda a: N.Col(a.ctypes.data, None, 0, n)
+    out_v, out_b = np.empty(n), np.zeros((n + 7) // 8, np.uint8)
+    oc = N.OutCol(out_v.ctypes.data, out_b.ctypes.data)
+    got = lambda: (out_v.copy(), np.unpackbits(out_b, bitorder="little")[:n].astype(bool))
+    cc, ch, cl, cv = col(c), col(h), col(l), col(v)
+    N.check(L.pqb_midpoint(eng._h, C.byref(cc), 14, C.byref(oc))); assert T.compare("midpoint", *got(), *pqo.midpoint(c, 14))[0] == 0
+    N.check(L.pqb_adosc(eng._h, C.byref(ch), C.byref(cl), C.byref(cc), C.byref(cv), 3, 10, C.byref(oc)))
+    assert T.compare("adosc", *got(), *pqo.adosc(h, l, c, v, 3, 10))[0] == 0
+    N.check(L.pqb_mom(eng._h, C.byref(cc), 10, C.byref(oc))); assert T.compare("mom", *got(), *pqo.mom(c, 10))[0] == 0
+    for kind in range(4):
+        N.check(L.pqb_roc(eng._h, C.byref(cc), 10, kind, C.byref(oc)))
+        assert T.compare("roc", *got(), *pqo.roc(c, 10, kind))[0] == 0
+    N.check(L.pqb_cmo(eng._h, C.byref(cc), 14, C.byref(oc))); assert T.compare("cmo", *got(), *pqo.cmo(c, 14))[0] == 0
+    N.check(L.pqb_mfi(eng._h, C.byref(ch), C.byref(cl), C.byref(cc), C.byref(cv), 14, C.byref(oc)))
+    assert T.compare("mfi", *got(), *pqo.mfi(h, l, c, v, 14))[0] == 0
+    N.check(L.pqb_cci(eng._h, C.byref(ch), C.byref(cl), C.byref(cc), 14, C.byref(oc)))
+    assert T.compare("cci", *got(), *pqo.cci(h, l, c, 14))[0] == 0
