@@ -306,7 +306,7 @@ def main():
                        % (ALGO_BYTES_PER_SYMBOL_BAR * S * N / 1e9),
                        "parallelism": "symbols sharded per GPU, no collective"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": "suite_fused_kernel<true>", "peak_source": peak_src,
+                         "traffic": traffic, "kernel": "suite_fused_kernel<true,false>", "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": ALGO_BYTES_PER_SYMBOL_BAR * S * N,
                          "kernel_ms": fused_ms_avg},
             "cpu_baseline": cpu,
