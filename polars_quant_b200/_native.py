@@ -106,6 +106,10 @@ def lib() -> C.CDLL:
         L.pqb_suite_time_host.argtypes = [C.c_void_p, C.POINTER(SuiteParams), C.c_int64, C.c_int, C.c_int,
                                           C.POINTER(C.c_float)]
         L.pqb_flush_l2.argtypes = [C.c_void_p]
+        L.pqb_multi_destroy.argtypes = [C.c_void_p]
+        L.pqb_multi_destroy.restype = None
+        L.pqb_multi_shard_count.argtypes = [C.c_void_p]
+        L.pqb_multi_run_host.argtypes = [C.c_void_p, C.POINTER(SuiteParams)]
         L.pqb_panel_last_launches.argtypes = [C.c_void_p]
         L.pqb_panel_tiled_shape.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
         L.pqb_suite_params_default.argtypes = [C.POINTER(SuiteParams)]

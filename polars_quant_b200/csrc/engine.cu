@@ -18,6 +18,7 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 using namespace pqb;
@@ -1363,4 +1364,102 @@ extern "C" int pqb_cci(pqb_engine *e, const pqb_col *h, const pqb_col *l, const 
     const pqb_col *c[] = {h, l, cl}; const int f[] = {PQB_HIGH, PQB_LOW, PQB_CLOSE}; const int o[] = {PQB_OUT_CCI};
     pqb_out_col *d[] = {out};
     return run_single(e, c, f, 3, NP_ERR, &sp, o, d, 1);
+}
+
+// ---------------------------------------------------------------------------------------
+// multi-GPU driver: symbol shards, one host thread per shard, no collective
+// ---------------------------------------------------------------------------------------
+struct pqb_multi {
+    struct Shard { int device = 0; int64_t lo = 0, hi = 0; pqb_engine *e = nullptr; pqb_panel *p = nullptr; };
+    std::vector<Shard> shards;
+    int64_t n_symbols = 0, n_bars = 0;
+};
+
+extern "C" void pqb_multi_destroy(pqb_multi *m) {
+    if (!m) return;
+    for (auto &s : m->shards) {
+        if (s.p) pqb_panel_destroy(s.p);
+        if (s.e) pqb_engine_destroy(s.e);
+    }
+    delete m;
+}
+
+extern "C" int pqb_multi_create(const int *devices, int n_devices, int64_t n_symbols, int64_t n_bars,
+                                uint32_t fields_mask, uint32_t outputs_mask, pqb_multi **out) {
+    if (!devices || n_devices <= 0 || !out) return fail(PQB_ERR_INVALID, "pqb_multi_create: bad argument");
+    *out = nullptr;
+    if (n_symbols <= 0 || n_bars <= 0) return fail(PQB_ERR_INVALID, "pqb_multi_create: bad shape");
+    pqb_multi *m = new pqb_multi();
+    m->n_symbols = n_symbols;
+    m->n_bars = n_bars;
+    // contiguous ranges of whole 32-symbol blocks, balanced to one block (polars_quant_b200/shard.py)
+    const int64_t n_blocks = (n_symbols + SYM - 1) / SYM;
+    const int64_t base = n_blocks / n_devices, extra = n_blocks % n_devices;
+    for (int r = 0; r < n_devices; ++r) {
+        const int64_t b_lo = r * base + std::min<int64_t>(r, extra), b_hi = b_lo + base + (r < extra ? 1 : 0);
+        pqb_multi::Shard s;
+        s.device = devices[r];
+        s.lo = std::min(b_lo * SYM, n_symbols);
+        s.hi = std::min(b_hi * SYM, n_symbols);
+        if (s.hi > s.lo) {
+            int rc = pqb_engine_create(s.device, &s.e);
+            if (!rc) rc = pqb_panel_create(s.e, s.hi - s.lo, n_bars, fields_mask, outputs_mask, 1, &s.p);
+            if (rc) { m->shards.push_back(s); pqb_multi_destroy(m); return rc; }
+        }
+        m->shards.push_back(s);
+    }
+    *out = m;
+    return PQB_OK;
+}
+
+extern "C" int pqb_multi_shard_count(const pqb_multi *m) { return m ? (int)m->shards.size() : 0; }
+
+extern "C" int pqb_multi_shard(const pqb_multi *m, int i, int *device, int64_t *lo, int64_t *hi, pqb_panel **panel) {
+    if (!m || i < 0 || i >= (int)m->shards.size()) return fail(PQB_ERR_INVALID, "pqb_multi_shard: bad index");
+    const auto &s = m->shards[(size_t)i];
+    if (device) *device = s.device;
+    if (lo) *lo = s.lo;
+    if (hi) *hi = s.hi;
+    if (panel) *panel = s.p;
+    return PQB_OK;
+}
+
+static const pqb_multi::Shard *shard_of(const pqb_multi *m, int64_t symbol) {
+    for (const auto &s : m->shards)
+        if (symbol >= s.lo && symbol < s.hi) return &s;
+    return nullptr;
+}
+
+extern "C" int pqb_multi_set_column(pqb_multi *m, int64_t symbol, int field, const double *values,
+                                    const uint8_t *validity, int64_t offset, int64_t len) {
+    const pqb_multi::Shard *s = m ? shard_of(m, symbol) : nullptr;
+    if (!s) return fail(PQB_ERR_INVALID, "pqb_multi_set_column: symbol %lld out of range", (long long)symbol);
+    return pqb_panel_set_column(s->p, symbol - s->lo, field, values, validity, offset, len);
+}
+
+extern "C" int pqb_multi_get_output(pqb_multi *m, int64_t symbol, int output, double *values, uint8_t *validity,
+                                    int64_t len) {
+    const pqb_multi::Shard *s = m ? shard_of(m, symbol) : nullptr;
+    if (!s) return fail(PQB_ERR_INVALID, "pqb_multi_get_output: symbol %lld out of range", (long long)symbol);
+    return pqb_panel_get_output(s->p, symbol - s->lo, output, values, validity, len);
+}
+
+extern "C" int pqb_multi_run_host(pqb_multi *m, const pqb_suite_params *params) {
+    if (!m || !params) return fail(PQB_ERR_INVALID, "pqb_multi_run_host: NULL argument");
+    const size_t n = m->shards.size();
+    std::vector<int> rcs(n, PQB_OK);
+    std::vector<std::string> errs(n);
+    std::vector<std::thread> th;
+    for (size_t i = 0; i < n; ++i) {
+        if (!m->shards[i].p) continue;
+        th.emplace_back([&, i] {
+            rcs[i] = pqb_suite_run_host(m->shards[i].p, params, 0);
+            if (rcs[i]) errs[i] = g_err;                  // the error text is thread-local: carry it over
+        });
+    }
+    for (auto &t : th) t.join();
+    for (size_t i = 0; i < n; ++i)
+        if (rcs[i]) return fail(rcs[i], "shard %zu (device %d, symbols [%lld, %lld)): %s", i, m->shards[i].device,
+                                (long long)m->shards[i].lo, (long long)m->shards[i].hi, errs[i].c_str());
+    return PQB_OK;
 }

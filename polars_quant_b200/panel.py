@@ -177,3 +177,53 @@ class Panel:
         tot = C.c_float()
         N.check(N.lib().pqb_suite_time_host(self._h, C.byref(params), chunk_symbols, warmup, iters, C.byref(tot)))
         return tot.value
+
+
+class MultiPanel:
+    """Multi-GPU driver (pqb_multi_*): one shard = engine + panel per listed device, symbols split in
+    contiguous whole-block ranges, one host thread per shard, no collective."""
+
+    def __init__(self, n_symbols: int, n_bars: int, devices, fields_mask: int = 0xF,
+                 outputs_mask: int = (1 << N.N_SUITE_OUTPUTS) - 1):
+        self.n_symbols, self.n_bars, self.outputs_mask = int(n_symbols), int(n_bars), outputs_mask
+        devs = (C.c_int * len(devices))(*devices)
+        self._h = C.c_void_p()
+        N.check(N.lib().pqb_multi_create(devs, len(devices), C.c_int64(n_symbols), C.c_int64(n_bars),
+                                         C.c_uint32(fields_mask), C.c_uint32(outputs_mask), C.byref(self._h)))
+
+    def close(self):
+        if self._h:
+            N.lib().pqb_multi_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def shards(self):
+        out = []
+        for i in range(N.lib().pqb_multi_shard_count(self._h)):
+            dev, lo, hi, ph = C.c_int(), C.c_int64(), C.c_int64(), C.c_void_p()
+            N.check(N.lib().pqb_multi_shard(self._h, i, C.byref(dev), C.byref(lo), C.byref(hi), C.byref(ph)))
+            out.append((dev.value, lo.value, hi.value))
+        return out
+
+    def set_column(self, symbol: int, field, values, validity=None, offset: int = 0):
+        f = Panel.FIELDS[field] if isinstance(field, str) else field
+        values = np.ascontiguousarray(values, dtype=np.float64)
+        vp = None if validity is None else np.ascontiguousarray(validity, dtype=np.uint8).ctypes.data_as(C.c_void_p)
+        N.check(N.lib().pqb_multi_set_column(self._h, C.c_int64(symbol), f, values.ctypes.data_as(C.c_void_p), vp,
+                                             C.c_int64(offset), C.c_int64(len(values) - offset)))
+
+    def run_host(self, params=None):
+        params = params or N.default_params()
+        N.check(N.lib().pqb_multi_run_host(self._h, C.byref(params)))
+
+    def get_output(self, symbol: int, k: int):
+        v = np.empty(self.n_bars)
+        b = np.zeros((self.n_bars + 7) // 8, np.uint8)
+        N.check(N.lib().pqb_multi_get_output(self._h, C.c_int64(symbol), k, v.ctypes.data_as(C.c_void_p),
+                                             b.ctypes.data_as(C.c_void_p), C.c_int64(self.n_bars)))
+        return v, np.unpackbits(b, bitorder="little")[:self.n_bars].astype(bool)

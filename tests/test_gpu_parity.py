@@ -389,3 +389,28 @@ def test_single_column_entry_points(pq):
     cn = N.Col(c_arr.ctypes.data, bm.ctypes.data, 0, n)
     vals, bits, oc = outs(1)
     assert L.pqb_rsi(eng._h, C.byref(cn), 14, C.byref(oc[0])) == -5
+
+
+def test_multi_gpu_driver_shards_by_symbol(pq):
+    """pqb_multi_*: the panel split over every visible GPU (two shards on one device when the box has a
+    single GPU), one host thread per shard, no collective; every symbol equals the oracle."""
+    import ctypes as C
+    from polars_quant_b200 import _native as N
+    n_dev = max(1, N.lib().pqb_device_count())
+    devices = list(range(n_dev)) if n_dev > 1 else [0, 0]
+    S, NB = 203, 600
+    d = synth.ohlcv(S, NB, seed=88)
+    mp = pq.MultiPanel(S, NB, devices)
+    sh = mp.shards()
+    assert sh[0][1] == 0 and sh[-1][2] == S and all(a[2] == b[1] for a, b in zip(sh, sh[1:]))
+    for s in range(S):
+        for f in ("close", "high", "low", "volume"):
+            mp.set_column(s, f, d[f][s])
+    mp.run_host()
+    out, ok = _oracle(d)
+    for s in range(0, S, 7):
+        for k, name in enumerate(pqo.OUTPUT_NAMES):
+            v, b = mp.get_output(s, k)
+            nbad, msg = T.compare(name, v, b, out[k][s], ok[k][s])
+            assert nbad == 0, f"symbol {s}: {msg}"
+    mp.close()
