@@ -221,6 +221,9 @@ def main():
         import torch
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
+        # NCCL prints its version banner (NCCL_DEBUG=VERSION/INFO in some images) on stdout: keep stdout
+        # to the one JSON line of the contract
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     import polars_quant_b200 as pq

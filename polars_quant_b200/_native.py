@@ -47,6 +47,18 @@ class SuiteParams(C.Structure):
                 ("cmo_period", C.c_int32), ("mfi_period", C.c_int32), ("cci_period", C.c_int32)]
 
 
+class CandleParams(C.Structure):
+    _fields_ = [("patterns", C.c_uint64), ("prices", C.c_uint32), ("pen_darkcloudcover", C.c_double),
+                ("pen_eveningdojistar", C.c_double), ("pen_eveningstar", C.c_double),
+                ("pen_morningdojistar", C.c_double), ("pen_morningstar", C.c_double), ("pen_piercing", C.c_double)]
+
+
+N_PATTERNS = 61
+N_PRICES = 5
+PRICE_NAMES = ["avgprice", "medprice", "typprice", "wclprice", "bop"]
+OPEN_, HIGH_, LOW_, CLOSE_ = 0, 1, 2, 3          # candle panel fields
+
+
 class Col(C.Structure):
     _fields_ = [("values", C.c_void_p), ("validity", C.c_void_p), ("offset", C.c_int64), ("len", C.c_int64)]
 
@@ -57,7 +69,8 @@ class OutCol(C.Structure):
 
 def build(force: bool = False) -> Path:
     """Compiles libpqb200.so in-tree with nvcc for sm_100a (works without a GPU)."""
-    srcs = list((_PKG / "csrc").glob("*.cu*")) + list((_PKG.parent / "include").glob("*.h"))
+    srcs = (list((_PKG / "csrc").glob("*.cu*")) + list((_PKG / "csrc").glob("*.inc")) +
+            list((_PKG.parent / "include").glob("*.h")))
     if force or not LIB_PATH.exists() or any(s.stat().st_mtime > LIB_PATH.stat().st_mtime for s in srcs):
         r = subprocess.run(["make", "-C", str(_PKG / "csrc"), "-B"], capture_output=True, text=True)
         if r.returncode != 0:
@@ -114,6 +127,34 @@ def lib() -> C.CDLL:
         L.pqb_panel_tiled_shape.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
         L.pqb_suite_params_default.argtypes = [C.POINTER(SuiteParams)]
         L.pqb_suite_params_default.restype = None
+        # candle engine
+        L.pqb_candle_params_default.argtypes = [C.POINTER(CandleParams)]
+        L.pqb_candle_params_default.restype = None
+        L.pqb_pattern_name.argtypes = [C.c_int]
+        L.pqb_pattern_name.restype = C.c_char_p
+        L.pqb_pattern_index.argtypes = [C.c_char_p]
+        L.pqb_candles_create.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_uint64, C.c_uint32, C.c_int,
+                                         C.POINTER(C.c_void_p)]
+        L.pqb_candles_destroy.argtypes = [C.c_void_p]
+        L.pqb_candles_destroy.restype = None
+        L.pqb_candles_pitch.argtypes = [C.c_void_p]
+        L.pqb_candles_pitch.restype = C.c_int64
+        L.pqb_candles_set_column.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64]
+        for name in ("pqb_candles_host_field", "pqb_candles_host_pattern", "pqb_candles_host_price",
+                     "pqb_candles_host_price_validity"):
+            f = getattr(L, name)
+            f.restype = C.c_void_p
+            f.argtypes = [C.c_void_p, C.c_int]
+        L.pqb_candles_run.argtypes = [C.c_void_p, C.POINTER(CandleParams)]
+        L.pqb_candles_run_host.argtypes = [C.c_void_p, C.POINTER(CandleParams)]
+        L.pqb_candles_get_pattern.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int64]
+        L.pqb_candles_get_price.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_int64]
+        L.pqb_candles_fill_synthetic.argtypes = [C.c_void_p, C.c_uint64, C.c_int]
+        L.pqb_candles_time.argtypes = [C.c_void_p, C.POINTER(CandleParams), C.c_int, C.c_int, C.POINTER(C.c_float)]
+        L.pqb_cdl.argtypes = [C.c_void_p, C.c_int, C.POINTER(Col), C.POINTER(Col), C.POINTER(Col), C.POINTER(Col),
+                              C.c_double, C.c_void_p]
+        L.pqb_price.argtypes = [C.c_void_p, C.c_int, C.POINTER(Col), C.POINTER(Col), C.POINTER(Col), C.POINTER(Col),
+                                C.POINTER(OutCol)]
         _lib = L
     return _lib
 

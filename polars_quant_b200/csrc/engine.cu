@@ -9,6 +9,7 @@
 // device, chunk by chunk, on the way in and out.
 #include "../../include/pqb200.h"
 #include "suite_kernel.cuh"
+#include "candles.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -89,6 +90,8 @@ struct pqb_engine {
     std::mutex mu;                       // guards the single-column scratch panel
     pqb_panel *scratch = nullptr;
     int64_t scratch_bars = 0;
+    pqb_candles *cscratch = nullptr;     // single-column scratch of the candle engine (candles_host.inc)
+    int64_t cscratch_bars = 0;
 };
 
 struct pqb_panel {
@@ -171,6 +174,7 @@ extern "C" void pqb_engine_destroy(pqb_engine *e) {
     if (!e) return;
     cudaSetDevice(e->device);
     if (e->scratch) pqb_panel_destroy(e->scratch);
+    if (e->cscratch) pqb_candles_destroy(e->cscratch);
     if (e->flush_buf) cudaFree(e->flush_buf);
     if (e->stream) cudaStreamDestroy(e->stream);
     if (e->h2d) cudaStreamDestroy(e->h2d);
@@ -1463,3 +1467,5 @@ extern "C" int pqb_multi_run_host(pqb_multi *m, const pqb_suite_params *params) 
                                 (long long)m->shards[i].lo, (long long)m->shards[i].hi, errs[i].c_str());
     return PQB_OK;
 }
+
+#include "candles_host.inc"

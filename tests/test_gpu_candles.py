@@ -1,0 +1,139 @@
+"""Candle engine on the GPU against the golden vectors made from the reference's own pattern.rs text:
+all 61 Int32 pattern columns, the price transforms and BOP, bit-exact, through the panel path, the
+single-column path and with the reference's null rules."""
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import polars_quant_b200 as pq
+from polars_quant_b200 import _native as N
+from polars_quant_b200 import candles
+
+pytestmark = pytest.mark.gpu
+ROOT = Path(__file__).resolve().parents[1]
+
+
+@pytest.fixture(scope="module")
+def g():
+    return np.load(ROOT / "tests" / "golden" / "candle_golden.npz")
+
+
+def _panel(g, **kw):
+    o, h, l, c = (g[k] for k in ("open", "high", "low", "close"))
+    p = candles.CandlePanel(o.shape[0], o.shape[1], **kw)
+    p.set_fields(o, h, l, c)
+    return p
+
+
+def test_all_61_patterns_match_the_reference_vectors(g):
+    p = _panel(g)
+    p.run_host()
+    names = [str(n) for n in g["names"]]
+    bad = []
+    for k, n in enumerate(names):
+        got = p.pattern(k)
+        if not np.array_equal(got, g["patterns"][k].astype(np.int32)):
+            i = np.argwhere(got != g["patterns"][k])[0]
+            bad.append((n, int((got != g["patterns"][k]).sum()), i.tolist()))
+    assert not bad, bad
+    p.close()
+
+
+def test_penetration_parameter(g):
+    p = _panel(g)
+    p.run_host(candles.default_params(penetration=float(g["penetration_value"])))
+    names = [str(n) for n in g["names"]]
+    for j, n in enumerate(str(x) for x in g["penetration_names"]):
+        assert np.array_equal(p.pattern(names.index(n)), g["patterns_pen"][j].astype(np.int32)), n
+    p.close()
+
+
+def test_price_transforms_and_bop_are_bit_exact(g):
+    p = _panel(g)
+    p.run_host()
+    for k, n in enumerate(N.PRICE_NAMES):
+        v, ok = p.price(k)
+        assert ok.all(), n
+        assert np.array_equal(v.view(np.uint64), g["prices"][k].view(np.uint64)), n
+    p.close()
+
+
+def test_partial_masks_and_device_resident_run_agree(g):
+    names = [str(n) for n in g["names"]]
+    want = [names.index(n) for n in ("cdlengulfing", "cdlhammer", "cdlrisefall3methods")]
+    mask = sum(1 << k for k in want)
+    p = _panel(g, patterns_mask=mask, prices_mask=1 << 4)
+    p.run_host()
+    for k in want:
+        assert np.array_equal(p.pattern(k), g["patterns"][k].astype(np.int32))
+    with pytest.raises(ValueError):
+        p.pattern(0)
+    with pytest.raises(N.PqbError):
+        p.run_host(candles.default_params())            # asks for planes this panel does not have
+    p.close()
+
+
+def test_single_column_entry_point_and_ragged_lengths(g):
+    names = [str(n) for n in g["names"]]
+    o, h, l, c = (g[k] for k in ("open", "high", "low", "close"))
+    for n in ("cdl3outside", "cdlbreakaway", "cdldoji", "cdlmorningstar"):
+        k = names.index(n)
+        for s in (0, 17, o.shape[0] - 1):
+            assert np.array_equal(candles.cdl(n, o[s], h[s], l[s], c[s]), g["patterns"][k][s]), (n, s)
+    # a column shorter than the lookback / not a multiple of the tile: prefix of the same series
+    k = names.index("cdlengulfing")
+    for m in (1, 2, 5, 33, 257, 300):
+        got = candles.cdl(k, o[3][:m], h[3][:m], l[3][:m], c[3][:m])
+        assert np.array_equal(got, g["patterns"][k][3][:m]), m      # patterns only look back
+    k = names.index("cdlpiercing")
+    j = [str(x) for x in g["penetration_names"]].index("cdlpiercing")
+    assert np.array_equal(candles.cdl(k, o[5], h[5], l[5], c[5], penetration=float(g["penetration_value"])), g["patterns_pen"][j][5])
+
+
+def test_null_rules(g):
+    o, h, l, c = (g[k][:8] for k in ("open", "high", "low", "close"))
+    ok_h = np.ones(h.shape, dtype=bool)
+    ok_h[2, 10:13] = False
+    ok_c = np.ones(c.shape, dtype=bool)
+    ok_c[5, 0] = False
+    p = candles.CandlePanel(8, o.shape[1], patterns_mask=0, prices_mask=0b01111)
+    p.set_fields(o, h, l, c, validity={1: ok_h, 3: ok_c})
+    p.run_host(candles.default_params(patterns=0, prices=0b01111))
+    avg, ok = p.price(0)
+    assert np.array_equal(ok, ok_h & ok_c)                              # price.rs:24-27 all four valid
+    med, okm = p.price(1)
+    assert np.array_equal(okm, ok_h)                                    # :44-47 high and low only
+    assert np.isnan(avg[~ok]).all() and np.array_equal(avg[ok], ((o + h + l + c) * 0.25)[ok])
+    p.close()
+    q = candles.CandlePanel(8, o.shape[1])
+    q.set_fields(o, h, l, c, validity={1: ok_h})
+    with pytest.raises(N.PqbError, match="not contiguous"):            # cdl* / bop: cont_slice()? pattern.rs:12
+        q.run_host()
+    q.close()
+
+
+def test_large_panel_properties():
+    """BASELINE config-2 shape on the device-resident path: determinism, value set, lookback zeros,
+    doji consistency between the flag-based patterns."""
+    S, n = 5000, 2520
+    names = candles.pattern_names()
+    ks = [names.index(x) for x in ("cdldoji", "cdllongleggeddoji", "cdlbreakaway", "cdlmarubozu", "cdlclosingmarubozu")]
+    mask = sum(1 << k for k in ks)
+    p = candles.CandlePanel(S, n, patterns_mask=mask, prices_mask=0b00011)
+    p.fill_synthetic(seed=9, to_host=True)
+    prm = candles.default_params(patterns=mask, prices=0b00011)
+    p.run_host(prm)
+    a = {k: p.pattern(k).copy() for k in ks}
+    p.run_host(prm)
+    for k in ks:
+        assert np.array_equal(a[k], p.pattern(k))
+        assert set(np.unique(a[k]).tolist()) <= {-100, 0, 100}
+    assert (a[names.index("cdlbreakaway")][:, :4] == 0).all()
+    assert (a[names.index("cdldoji")] != 0).sum() > 1000
+    assert ((a[names.index("cdllongleggeddoji")] != 0) <= (a[names.index("cdldoji")] != 0)).all()
+    assert ((a[names.index("cdlmarubozu")] != 0) <= (a[names.index("cdlclosingmarubozu")] != 0)).all()
+    o, h, l, c = (p.host_field(f) for f in range(4))
+    avg, ok = p.price(0)
+    assert ok.all() and np.array_equal(avg, (o + h + l + c) * 0.25)
+    p.close()
