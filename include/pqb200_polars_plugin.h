@@ -123,6 +123,31 @@ PQB_POLARS_PLUGIN(adosc)     /* :34   (high, low, close, volume; fastperiod=3, s
 PQB_POLARS_PLUGIN(stoch)     /* (high, low, close; fastk_period=5, slowk_period=3, slowd_period=3) -> struct stoch{slowk, slowd} */
 PQB_POLARS_PLUGIN(kdj)       /* (high, low, close; fastk_period=9, k_period=3, d_period=3) -> struct kdj{k, d, j} */
 
+/* candle functions: pattern.rs:9-2065 `#[polars_expr(output_type=Int32)] pub fn cdl*(inputs)`
+ * (open, high, low, close [, penetration Float64 literal]) -> Int32 in {-100, 0, 100}, in the reference's order of
+ * definition = pattern ids 0..60 of pqb200.h; price.rs:10-91 and momentum.rs:113 (bop) -> Float64 */
+#define PQB_CDL_LIST(X)                                                                                      \
+    X(cdl2crows) X(cdl3blackcrows) X(cdl3inside) X(cdl3linestrike) X(cdl3outside) X(cdl3starsinsouth)        \
+    X(cdl3whitesoldiers) X(cdlabandonedbaby) X(cdladvanceblock) X(cdlbelthold) X(cdlbreakaway)               \
+    X(cdlclosingmarubozu) X(cdlconcealbabyswall) X(cdlcounterattack) X(cdldarkcloudcover) X(cdldoji)         \
+    X(cdldojistar) X(cdldragonflydoji) X(cdlengulfing) X(cdleveningdojistar) X(cdleveningstar)               \
+    X(cdlgapsidesidewhite) X(cdlgravestonedoji) X(cdlhammer) X(cdlhangingman) X(cdlharami) X(cdlharamicross) \
+    X(cdlhighwave) X(cdlhikkake) X(cdlhikkakemod) X(cdlhomingpigeon) X(cdlidentical3crows) X(cdlinneck)      \
+    X(cdlinvertedhammer) X(cdlkicking) X(cdlkickingbylength) X(cdlladderbottom) X(cdllongleggeddoji)         \
+    X(cdllongline) X(cdlmarubozu) X(cdlmatchinglow) X(cdlmathold) X(cdlmorningdojistar) X(cdlmorningstar)    \
+    X(cdlonneck) X(cdlpiercing) X(cdlrickshawman) X(cdlrisefall3methods) X(cdlseparatinglines)               \
+    X(cdlshootingstar) X(cdlshortline) X(cdlspinningtop) X(cdlstalledpattern) X(cdlsticksandwich)            \
+    X(cdltakuri) X(cdltasukigap) X(cdlthrusting) X(cdltristar) X(cdlunique3river) X(cdlupsidegap2crows)      \
+    X(cdlxsidegap3methods)
+#define X(n) PQB_POLARS_PLUGIN(n)
+PQB_CDL_LIST(X)
+#undef X
+PQB_POLARS_PLUGIN(avgprice)  /* price.rs:10   (open, high, low, close) */
+PQB_POLARS_PLUGIN(medprice)  /* price.rs:35   (high, low) */
+PQB_POLARS_PLUGIN(typprice)  /* price.rs:55   (high, low, close) */
+PQB_POLARS_PLUGIN(wclprice)  /* price.rs:75   (high, low, close) */
+PQB_POLARS_PLUGIN(bop)       /* momentum.rs:113 (open, high, low, close) */
+
 #ifdef __cplusplus
 }
 #endif

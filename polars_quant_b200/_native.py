@@ -150,6 +150,7 @@ def lib() -> C.CDLL:
         L.pqb_candles_get_pattern.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int64]
         L.pqb_candles_get_price.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_int64]
         L.pqb_candles_fill_synthetic.argtypes = [C.c_void_p, C.c_uint64, C.c_int]
+        L.pqb_candles_fill_random_walk.argtypes = [C.c_void_p, C.c_uint64, C.c_double, C.c_int]
         L.pqb_candles_time.argtypes = [C.c_void_p, C.POINTER(CandleParams), C.c_int, C.c_int, C.POINTER(C.c_float)]
         L.pqb_cdl.argtypes = [C.c_void_p, C.c_int, C.POINTER(Col), C.POINTER(Col), C.POINTER(Col), C.POINTER(Col),
                               C.c_double, C.c_void_p]

@@ -99,6 +99,9 @@ class CandlePanel:
     def fill_synthetic(self, seed: int = 1, to_host: bool = False):
         N.check(N.lib().pqb_candles_fill_synthetic(self._h, seed, 1 if to_host else 0))
 
+    def fill_random_walk(self, seed: int = 0xC0FFEE, sigma: float = 0.02, to_host: bool = False):
+        N.check(N.lib().pqb_candles_fill_random_walk(self._h, seed, sigma, 1 if to_host else 0))
+
     def time_device(self, params=None, warmup: int = 3, iters: int = 10) -> float:
         """Milliseconds of `iters` back-to-back fused candle launches on the device-resident panel."""
         p = params or default_params(self.patterns_mask, self.prices_mask)

@@ -60,6 +60,7 @@ struct CandleArgs {
     double *price[N_PRICES];         // f64 planes or nullptr
     uint32_t *vprice[N_PRICES];      // validity words of the price planes or nullptr
     double pen[N_PEN];
+    size_t pat_stride;               // ALL specialisation: pattern k's plane = pat[0] + k * pat_stride (one allocation)
     int n_symbols, n_bars, pitch, words_per_row;
     int symbol0;                     // first symbol of this launch (chunked host pipeline)
 };
@@ -108,7 +109,9 @@ __device__ __forceinline__ unsigned classify(double o, double h, double l, doubl
 
 __device__ __forceinline__ void st_i32(int32_t *p, int v) { __stcs(p, v); }
 
-// grid = (ceil(n_bars / CANDLE_TILE), symbols of this launch), CANDLE_TILE threads
+// grid = (ceil(n_bars / CANDLE_TILE), symbols of this launch), CANDLE_TILE threads.
+// ALL: every pattern enabled and the 61 planes are one allocation (no mask tests, one base pointer).
+template <bool ALL>
 __global__ void __launch_bounds__(CANDLE_TILE) candle_kernel(const __grid_constant__ CandleArgs A, const uint64_t pmask) {
     __shared__ double so[CANDLE_TILE + CANDLE_HALO], sh[CANDLE_TILE + CANDLE_HALO], sl[CANDLE_TILE + CANDLE_HALO],
         sc[CANDLE_TILE + CANDLE_HALO];
@@ -175,7 +178,7 @@ __global__ void __launch_bounds__(CANDLE_TILE) candle_kernel(const __grid_consta
         const double diff = h0 - l0;                                        // bop momentum.rs:113-135
         emit(4, (diff == 0.0) ? 0.0 : (c0 - o0) / ((diff == 0.0) ? 1.0 : diff), ko && kh && kl && kc);
     }
-    if (!live || pmask == 0) return;
+    if (!ALL && pmask == 0) return;
 
     // ---- the window: k bars back = index tid + HALO - k
     const int q = tid + CANDLE_HALO;
@@ -201,150 +204,145 @@ __global__ void __launch_bounds__(CANDLE_TILE) candle_kernel(const __grid_consta
     const bool maru0 = HAS(f0, CF_LONG | CF_VSUS | CF_VSDS), maru1 = HAS(f1, CF_LONG | CF_VSUS | CF_VSDS);
     const bool lb1 = i >= 1, lb2 = i >= 2, lb3 = i >= 3, lb4 = i >= 4;
     const size_t at = row + i;
-    // `up` -> +100, else `dn` -> -100, else 0; stored only for enabled patterns
-#define EMIT(id, up, dn)                                                        \
-    if (pmask >> (id) & 1) st_i32(A.pat[id] + at, (up) ? 100 : ((dn) ? -100 : 0));
+    int32_t *const pbase = A.pat[0] + at;
+    const size_t pstride = A.pat_stride;
+    // `up` -> +100, else `dn` -> -100, else 0.  (A warp-voted early-out on the flag preconditions was measured:
+    // on random-walk data almost every 32-bar warp has a lane that passes, and the votes cost more than they save.)
+#define EMIT(id, up, dn)                                                                   \
+    if (ALL || (pmask >> (id) & 1)) {                                                      \
+        if (live) st_i32(ALL ? pbase + (size_t)(id) * pstride : A.pat[id] + at, (up) ? 100 : ((dn) ? -100 : 0)); \
+    }
+    const bool bear3 = f3 & CF_BEAR, bull3 = f3 & CF_BULL, short2 = f2 & CF_SHORT, short3 = f3 & CF_SHORT, doji2 = f2 & CF_DOJI;
+    const bool long0 = f0 & CF_LONG, long1 = f1 & CF_LONG, long2 = f2 & CF_LONG, long4 = f4 & CF_LONG;
 
-    EMIT(P_cdl2crows, false,                                                                       // pattern.rs:10 (can never fire:
+    EMIT(P_cdl2crows, false,                                      // pattern.rs:10 (can never fire:
          lb2 && lbull2 && bear1 && o1 > c2 && bear0 && (o0 > o1 && o0 < c1) && (c0 > o2 && c0 < c2))   //  o0 > o1 && o0 < c1 with c1 < o1)
-    EMIT(P_cdl3blackcrows, false,                                                                  // :43
+    EMIT(P_cdl3blackcrows, false,                               // :43
          lb2 && lbear2 && lbear1 && lbear0 && (o1 < o2 && o1 > c2) && (o0 < o1 && o0 > c1) && (c1 < c2 && c0 < c1))
-    EMIT(P_cdl3inside,                                                                             // :76
+    EMIT(P_cdl3inside,                                                               // :76
          lb2 && lbear2 && bull1 && c1 < o2 && o1 > c2 && bull0 && c0 > o2,
          lb2 && lbull2 && bear1 && o1 < c2 && c1 > o2 && bear0 && c0 < o2)
-    {                                                                                              // :114 cdl3linestrike
-        const bool bear3 = f3 & CF_BEAR, bull3 = f3 & CF_BULL;
-        const bool up = lb3 && bear3 && bear2 && bear1 && c2 < c3 && c1 < c2 && o2 > c3 && o2 < o3 && o1 > c2 && o1 < o2 &&
-                        bull0 && o0 < c1 && c0 > o3;
-        const bool dn = lb3 && bull3 && bull2 && bull1 && c2 > c3 && c1 > c2 && o2 < c3 && o2 > o3 && o1 < c2 && o1 > o2 &&
-                        bear0 && o0 > c1 && c0 < o3;
-        EMIT(P_cdl3linestrike, up, dn)
-    }
-    EMIT(P_cdl3outside,                                                                            // :160
+    EMIT(P_cdl3linestrike,   // :114
+         lb3 && bear3 && bear2 && bear1 && c2 < c3 && c1 < c2 && o2 > c3 && o2 < o3 && o1 > c2 && o1 < o2 && bull0 && o0 < c1 && c0 > o3,
+         lb3 && bull3 && bull2 && bull1 && c2 > c3 && c1 > c2 && o2 < c3 && o2 > o3 && o1 < c2 && o1 > o2 && bear0 && o0 > c1 && c0 < o3)
+    EMIT(P_cdl3outside,           // :160
          lb2 && bear2 && bull1 && o1 <= c2 && c1 >= o2 && bull0 && c0 > c1,
          lb2 && bull2 && bear1 && o1 >= c2 && c1 <= o2 && bear0 && c0 < c1)
-    EMIT(P_cdl3starsinsouth,                                                                       // :194
+    EMIT(P_cdl3starsinsouth,           // :194
          lb2 && lbear2 && (f2 & CF_LDS) && bear1 && l1 > l2 && c1 > c2 && bear0 && short0 && h0 < h1 && l0 > l1, false)
-    EMIT(P_cdl3whitesoldiers,                                                                      // :234
+    EMIT(P_cdl3whitesoldiers,                                   // :234
          lb2 && lbull2 && lbull1 && lbull0 && (o1 > o2 && o1 <= c2) && (o0 > o1 && o0 <= c1) && (c1 > c2 && c0 > c1), false)
-    EMIT(P_cdlabandonedbaby,                                                                       // :268
+    EMIT(P_cdlabandonedbaby,                                                // :268
          lb2 && lbear2 && doji1 && h1 < l2 && bull0 && l0 > h1,
          lb2 && lbull2 && doji1 && l1 > h2 && bear0 && h0 < l1)
-    EMIT(P_cdladvanceblock, false,                                                                 // :309
+    EMIT(P_cdladvanceblock, false,                                // :309
          lb2 && lbull2 && bull1 && bull0 && (o1 > o2 && o1 <= c2) && (o0 > o1 && o0 <= c1) && (c1 > c2 && c0 > c1) && b0 < b1)
-    EMIT(P_cdlbelthold, lbull0 && (f0 & CF_VSDS), lbear0 && (f0 & CF_VSUS))                        // :345
-    EMIT(P_cdlbreakaway,                                                                           // :373
-         lb4 && lbear4 && (f3 & CF_BEAR) && o3 < c4 && c2 < c3 && bull0 && c0 > o3 && c0 < c4,
-         lb4 && lbull4 && (f3 & CF_BULL) && o3 > c4 && c2 > c3 && bear0 && c0 < o3 && c0 > c4)
-    EMIT(P_cdlclosingmarubozu, lbull0 && (f0 & CF_VSUS), lbear0 && (f0 & CF_VSDS))                 // :414
-    EMIT(P_cdlconcealbabyswall,                                                                    // :442
+    EMIT(P_cdlbelthold, lbull0 && (f0 & CF_VSDS), lbear0 && (f0 & CF_VSUS))                       // :345
+    EMIT(P_cdlbreakaway,                                                             // :373
+         lb4 && lbear4 && bear3 && o3 < c4 && c2 < c3 && bull0 && c0 > o3 && c0 < c4,
+         lb4 && lbull4 && bull3 && o3 > c4 && c2 > c3 && bear0 && c0 < o3 && c0 > c4)
+    EMIT(P_cdlclosingmarubozu, lbull0 && (f0 & CF_VSUS), lbear0 && (f0 & CF_VSDS))                // :414
+    EMIT(P_cdlconcealbabyswall,
          lb3 && HAS(f3, CF_BEAR | CF_LONG | CF_VSUS | CF_VSDS) && HAS(f2, CF_BEAR | CF_LONG | CF_VSUS | CF_VSDS) && c2 < c3 &&
              bear1 && h1 > c2 && lbear0 && o0 > h1 && c0 < l2, false)
-    EMIT(P_cdlcounterattack,                                                                       // :487
+    EMIT(P_cdlcounterattack,                                                // :487
          lb1 && lbear1 && lbull0 && NEAR(c0, c1), lb1 && lbull1 && lbear0 && NEAR(c0, c1))
-    EMIT(P_cdldarkcloudcover, false,                                                               // :519
+    EMIT(P_cdldarkcloudcover, false,                                       // :519
          lb1 && lbull1 && bear0 && o0 > c1 && c0 < (c1 - (b1 * A.pen[PEN_DARKCLOUDCOVER])) && c0 > o1)
-    EMIT(P_cdldoji, doji0, false)                                                                  // :553
-    {                                                                                              // :578 cdldojistar
-        const double mid = (o0 + c0) / 2.0;
-        EMIT(P_cdldojistar, lb1 && lbear1 && doji0 && mid < c1, lb1 && lbull1 && doji0 && mid > c1)
-    }
-    EMIT(P_cdldragonflydoji, HAS(f0, CF_DOJI | CF_LDS | CF_VSUS), false)                           // :610
-    EMIT(P_cdlengulfing,                                                                           // :635
+    EMIT(P_cdldoji, doji0, false)                                                                 // :553
+    EMIT(P_cdldojistar,                                                     // :578
+         lb1 && lbear1 && doji0 && ((o0 + c0) / 2.0) < c1, lb1 && lbull1 && doji0 && ((o0 + c0) / 2.0) > c1)
+    EMIT(P_cdldragonflydoji, HAS(f0, CF_DOJI | CF_LDS | CF_VSUS), false)                          // :610
+    EMIT(P_cdlengulfing,                            // :635
          lb1 && bear1 && bull0 && o0 <= c1 && c0 >= o1 && (o0 < c1 || c0 > o1),
          lb1 && bull1 && bear0 && o0 >= c1 && c0 <= o1 && (o0 > c1 || c0 < o1))
-    EMIT(P_cdleveningdojistar, false,                                                              // :665
+    EMIT(P_cdleveningdojistar, false,                             // :665
          lb2 && lbull2 && doji1 && fmin(o1, c1) > c2 && bear0 && c0 < (c2 - (b2 * A.pen[PEN_EVENINGDOJISTAR])))
-    EMIT(P_cdleveningstar, false,                                                                  // :703
+    EMIT(P_cdleveningstar, false,                                // :703
          lb2 && lbull2 && short1 && fmin(o1, c1) > c2 && bear0 && c0 < (c2 - (b2 * A.pen[PEN_EVENINGSTAR])))
-    {                                                                                              // :739 cdlgapsidesidewhite
-        const bool both = bull1 && bull0 && NEAR(b0, b1) && NEAR(o0, o1);
-        EMIT(P_cdlgapsidesidewhite, lb2 && bull2 && o1 > c2 && both, lb2 && bear2 && c1 < c2 && both)
-    }
-    EMIT(P_cdlgravestonedoji, false, HAS(f0, CF_DOJI | CF_LUS | CF_VSDS))                          // :777
-    EMIT(P_cdlhammer, lb1 && HAS(f0, CF_SHORT | CF_LDS | CF_VSUS) && bear1, false)                 // :802
-    EMIT(P_cdlhangingman, false, lb1 && HAS(f0, CF_SHORT | CF_LDS | CF_VSUS) && bull1)             // :832
-    EMIT(P_cdlharami,                                                                              // :862
+    EMIT(P_cdlgapsidesidewhite,                                             // :739
+         lb2 && bull2 && o1 > c2 && bull1 && bull0 && NEAR(b0, b1) && NEAR(o0, o1),
+         lb2 && bear2 && c1 < c2 && bull1 && bull0 && NEAR(b0, b1) && NEAR(o0, o1))
+    EMIT(P_cdlgravestonedoji, false, HAS(f0, CF_DOJI | CF_LUS | CF_VSDS))                         // :777
+    EMIT(P_cdlhammer, lb1 && HAS(f0, CF_SHORT | CF_LDS | CF_VSUS) && bear1, false)                // :802
+    EMIT(P_cdlhangingman, false, lb1 && HAS(f0, CF_SHORT | CF_LDS | CF_VSUS) && bull1)            // :832
+    EMIT(P_cdlharami,                                                      // :862
          lb1 && lbear1 && bull0 && short0 && o0 > c1 && c0 < o1,
          lb1 && lbull1 && bear0 && short0 && o0 < c1 && c0 > o1)
-    EMIT(P_cdlharamicross,                                                                         // :896
+    EMIT(P_cdlharamicross,                                                  // :896
          lb1 && lbear1 && doji0 && fmax(o0, c0) < o1 && fmin(o0, c0) > c1,
          lb1 && lbull1 && doji0 && fmax(o0, c0) < c1 && fmin(o0, c0) > o1)
     EMIT(P_cdlhighwave, HAS(f0, CF_SHORT | CF_LUS | CF_LDS) && bull0, HAS(f0, CF_SHORT | CF_LUS | CF_LDS) && bear0)   // :929
     {                                                                                              // :956, :987 hikkake / hikkakemod
         const bool inside12 = h1 < h2 && l1 > l2;
         EMIT(P_cdlhikkake, lb2 && inside12 && c0 > h2 && bull0, lb2 && inside12 && c0 < l2 && bear0)
-        const bool two = (h2 < h3 && l2 > l3) && inside12;
-        EMIT(P_cdlhikkakemod, lb3 && two && c0 > h3 && bull0, lb3 && two && c0 < l3 && bear0)
+        EMIT(P_cdlhikkakemod,
+             lb3 && (h2 < h3 && l2 > l3) && inside12 && c0 > h3 && bull0, lb3 && (h2 < h3 && l2 > l3) && inside12 && c0 < l3 && bear0)
     }
-    EMIT(P_cdlhomingpigeon, lb1 && lbear1 && bear0 && short0 && o0 < o1 && c0 > c1, false)         // :1021
-    EMIT(P_cdlidentical3crows, false,                                                              // :1048
+    EMIT(P_cdlhomingpigeon,                                      // :1021
+         lb1 && lbear1 && bear0 && short0 && o0 < o1 && c0 > c1, false)
+    EMIT(P_cdlidentical3crows, false,                           // :1048
          lb2 && lbear2 && lbear1 && lbear0 && EQUAL(o1, c2) && EQUAL(o0, c1) && (c1 < c2 && c0 < c1))
-    EMIT(P_cdlinneck, false, lb1 && lbear1 && bull0 && o0 < c1 && NEAR(c0, c1))                    // :1083
-    EMIT(P_cdlinvertedhammer, lb1 && HAS(f0, CF_SHORT | CF_LUS | CF_VSDS) && bear1, false)         // :1111
+    EMIT(P_cdlinneck, false, lb1 && lbear1 && bull0 && o0 < c1 && NEAR(c0, c1))   // :1083
+    EMIT(P_cdlinvertedhammer, lb1 && HAS(f0, CF_SHORT | CF_LUS | CF_VSDS) && bear1, false)        // :1111
     {                                                                                              // :1141, :1183 kicking / kickingbylength
-        const bool bull_kick = lb1 && bear1 && maru1 && bull0 && maru0 && o0 > o1;
-        const bool bear_kick = lb1 && bull1 && maru1 && bear0 && maru0 && o0 < o1;
+        const bool pre = lb1 && maru1 && maru0;
+        const bool bull_kick = pre && bear1 && bull0 && o0 > o1;
+        const bool bear_kick = pre && bull1 && bear0 && o0 < o1;
         EMIT(P_cdlkicking, bull_kick, bear_kick)
-        const bool ge = b0 >= b1;
-        const bool bull_longer = bull_kick && ge, bear_longer = bear_kick && ge;
-        EMIT(P_cdlkickingbylength, bull_longer || (bull_kick && !bear_longer), bear_longer || (bear_kick && !bull_longer))
+        EMIT(P_cdlkickingbylength, (bull_kick && b0 >= b1) || (bull_kick && !(bear_kick && b0 >= b1)),
+             (bear_kick && b0 >= b1) || (bear_kick && !(bull_kick && b0 >= b1)))
     }
-    EMIT(P_cdlladderbottom,                                                                        // :1229
-         lb4 && lbear4 && ((f3 & CF_BEAR) && c3 < c4) && (bear2 && c2 < c3) && bear1 && (f1 & CF_LUS) && (bull0 && o0 > o1), false)
-    EMIT(P_cdllongleggeddoji, HAS(f0, CF_DOJI | CF_LUS | CF_LDS), false)                           // :1267
-    EMIT(P_cdllongline, HAS(f0, CF_LONG | CF_SUS | CF_SDS) && bull0, HAS(f0, CF_LONG | CF_SUS | CF_SDS) && bear0)     // :1292
-    EMIT(P_cdlmarubozu, maru0 && bull0, maru0 && bear0)                                            // :1321
-    EMIT(P_cdlmatchinglow, lb1 && lbear1 && bear0 && EQUAL(c0, c1), false)                         // :1349
-    EMIT(P_cdlmathold,                                                                             // :1376
-         lb4 && lbull4 && ((f3 & CF_SHORT) && o3 > c4) && (f2 & CF_SHORT) && short1 && (l3 > o4 && l2 > o4 && l1 > o4) &&
-             (bull0 && c0 > c4), false)
-    EMIT(P_cdlmorningdojistar,                                                                     // :1416
+    EMIT(P_cdlladderbottom,    // :1229
+         lb4 && lbear4 && (bear3 && c3 < c4) && (bear2 && c2 < c3) && bear1 && (f1 & CF_LUS) && (bull0 && o0 > o1), false)
+    EMIT(P_cdllongleggeddoji, HAS(f0, CF_DOJI | CF_LUS | CF_LDS), false)                          // :1267
+    EMIT(P_cdllongline, HAS(f0, CF_LONG | CF_SUS | CF_SDS) && bull0, HAS(f0, CF_LONG | CF_SUS | CF_SDS) && bear0)    // :1292
+    EMIT(P_cdlmarubozu, maru0 && bull0, maru0 && bear0)                                           // :1321
+    EMIT(P_cdlmatchinglow, lb1 && lbear1 && bear0 && EQUAL(c0, c1), false) // :1349
+    EMIT(P_cdlmathold,                       // :1376
+         lb4 && lbull4 && (short3 && o3 > c4) && short2 && short1 && (l3 > o4 && l2 > o4 && l1 > o4) && (bull0 && c0 > c4), false)
+    EMIT(P_cdlmorningdojistar,                                    // :1416
          lb2 && lbear2 && doji1 && fmax(o1, c1) < c2 && bull0 && c0 > (c2 + (b2 * A.pen[PEN_MORNINGDOJISTAR])), false)
-    EMIT(P_cdlmorningstar,                                                                         // :1454
+    EMIT(P_cdlmorningstar,                                       // :1454
          lb2 && lbear2 && short1 && fmax(o1, c1) < c2 && bull0 && c0 > (c2 + (b2 * A.pen[PEN_MORNINGSTAR])), false)
-    EMIT(P_cdlonneck, false, lb1 && lbear1 && bull0 && o0 < c1 && NEAR(c0, l1))                    // :1490
-    EMIT(P_cdlpiercing,                                                                            // :1519
+    EMIT(P_cdlonneck, false, lb1 && lbear1 && bull0 && o0 < c1 && NEAR(c0, l1))   // :1490
+    EMIT(P_cdlpiercing,                                                    // :1519
          lb1 && lbear1 && bull0 && o0 < c1 && c0 > (c1 + (b1 * A.pen[PEN_PIERCING])) && c0 < o1, false)
-    EMIT(P_cdlrickshawman, HAS(f0, CF_DOJI | CF_LUS | CF_LDS) && NEAR(us0, ls0), false)            // :1553
-    {                                                                                              // :1581 cdlrisefall3methods
-        const bool shorts = (f3 & CF_SHORT) && (f2 & CF_SHORT) && short1;
-        const bool inside = h3 < h4 && h2 < h4 && h1 < h4 && l3 > l4 && l2 > l4 && l1 > l4;
-        EMIT(P_cdlrisefall3methods, lb4 && lbull4 && shorts && inside && lbull0 && c0 > c4,
-             lb4 && lbear4 && shorts && inside && lbear0 && c0 < c4)
-    }
-    EMIT(P_cdlseparatinglines, lb1 && lbear1 && lbull0 && EQUAL(o0, o1), lb1 && lbull1 && lbear0 && EQUAL(o0, o1))    // :1647
-    EMIT(P_cdlshootingstar, false, lb1 && HAS(f0, CF_SHORT | CF_LUS | CF_VSDS) && bull1)           // :1679
-    EMIT(P_cdlshortline, HAS(f0, CF_SHORT | CF_SUS | CF_SDS) && bull0, HAS(f0, CF_SHORT | CF_SUS | CF_SDS) && bear0)  // :1709
-    EMIT(P_cdlspinningtop, HAS(f0, CF_SHORT | CF_USGB | CF_LSGB) && bull0, HAS(f0, CF_SHORT | CF_USGB | CF_LSGB) && bear0)   // :1738
-    EMIT(P_cdlstalledpattern, false,                                                               // :1766
+    EMIT(P_cdlrickshawman,                                     // :1553
+         HAS(f0, CF_DOJI | CF_LUS | CF_LDS) && NEAR(us0, ls0), false)
+    EMIT(P_cdlrisefall3methods,               // :1581
+         lb4 && lbull4 && short3 && short2 && short1 && (h3 < h4 && h2 < h4 && h1 < h4 && l3 > l4 && l2 > l4 && l1 > l4) && lbull0 && c0 > c4,
+         lb4 && lbear4 && short3 && short2 && short1 && (h3 < h4 && h2 < h4 && h1 < h4 && l3 > l4 && l2 > l4 && l1 > l4) && lbear0 && c0 < c4)
+    EMIT(P_cdlseparatinglines,                                              // :1647
+         lb1 && lbear1 && lbull0 && EQUAL(o0, o1), lb1 && lbull1 && lbear0 && EQUAL(o0, o1))
+    EMIT(P_cdlshootingstar, false, lb1 && HAS(f0, CF_SHORT | CF_LUS | CF_VSDS) && bull1)          // :1679
+    EMIT(P_cdlshortline, HAS(f0, CF_SHORT | CF_SUS | CF_SDS) && bull0, HAS(f0, CF_SHORT | CF_SUS | CF_SDS) && bear0) // :1709
+    EMIT(P_cdlspinningtop, HAS(f0, CF_SHORT | CF_USGB | CF_LSGB) && bull0, HAS(f0, CF_SHORT | CF_USGB | CF_LSGB) && bear0)  // :1738
+    EMIT(P_cdlstalledpattern, false,                   // :1766
          lb2 && lbull2 && (lbull1 && c1 > c2) && (bull0 && short0 && c0 > c1) && (o0 > o1 && o0 <= c1))
-    EMIT(P_cdlsticksandwich, lb2 && lbear2 && lbull1 && o1 > c2 && lbear0 && EQUAL(c0, c2), false) // :1797
-    EMIT(P_cdltakuri, HAS(f0, CF_DOJI | CF_VLDS | CF_VSUS), false)                                 // :1831
-    EMIT(P_cdltasukigap,                                                                           // :1856
+    EMIT(P_cdlsticksandwich,                                    // :1797
+         lb2 && lbear2 && lbull1 && o1 > c2 && lbear0 && EQUAL(c0, c2), false)
+    EMIT(P_cdltakuri, HAS(f0, CF_DOJI | CF_VLDS | CF_VSUS), false)                                // :1831
+    EMIT(P_cdltasukigap,          // :1856
          lb2 && bull2 && bull1 && o1 > c2 && bear0 && o0 > o1 && o0 < c1 && c0 > o2 && c0 < c2,
          lb2 && bear2 && bear1 && o1 < c2 && bull0 && o0 < o1 && o0 > c1 && c0 < o2 && c0 > c2)
-    {                                                                                              // :1894 cdlthrusting
-        const double midpoint = c1 + (b1 * 0.5);
-        EMIT(P_cdlthrusting, false, lb1 && lbear1 && bull0 && o0 < c1 && c0 > c1 && c0 < midpoint)
-    }
-    {                                                                                              // :1922 cdltristar
-        const double m2 = (o2 + c2) / 2.0, m1 = (o1 + c1) / 2.0, m0 = (o0 + c0) / 2.0;
-        const bool three = lb2 && (f2 & CF_DOJI) && doji1 && doji0;
-        EMIT(P_cdltristar, three && m1 < m2 && m0 > m1, three && m1 > m2 && m0 < m1)
-    }
-    EMIT(P_cdlunique3river,                                                                        // :1964
+    EMIT(P_cdlthrusting, false,                                            // :1894
+         lb1 && lbear1 && bull0 && o0 < c1 && c0 > c1 && c0 < (c1 + (b1 * 0.5)))
+    EMIT(P_cdltristar,                                             // :1922
+         lb2 && doji2 && doji1 && doji0 && ((o1 + c1) / 2.0) < ((o2 + c2) / 2.0) && ((o0 + c0) / 2.0) > ((o1 + c1) / 2.0),
+         lb2 && doji2 && doji1 && doji0 && ((o1 + c1) / 2.0) > ((o2 + c2) / 2.0) && ((o0 + c0) / 2.0) < ((o1 + c1) / 2.0))
+    EMIT(P_cdlunique3river,                             // :1964
          lb2 && lbear2 && (bear1 && l1 < l2 && c1 > l1) && (o1 < o2 && o1 > c2) && (bull0 && short0 && c0 < c1), false)
-    EMIT(P_cdlupsidegap2crows, false,                                                              // :1997
+    EMIT(P_cdlupsidegap2crows, false,                             // :1997
          lb2 && lbull2 && (bear1 && o1 > c2 && c1 > c2) && (bear0 && o0 > o1 && c0 > c2 && c0 < c1))
-    EMIT(P_cdlxsidegap3methods,                                                                    // :2027
+    EMIT(P_cdlxsidegap3methods,   // :2027
          lb2 && bull2 && bull1 && o1 > c2 && bear0 && o0 < c1 && o0 > o1 && c0 > o2 && c0 < c2,
          lb2 && bear2 && bear1 && o1 < c2 && bull0 && o0 > c1 && o0 < o1 && c0 < o2 && c0 > c2)
 #undef EMIT
 #undef HAS
 #undef NEAR
 #undef EQUAL
-    (void)h3; (void)h4; (void)l3; (void)l4; (void)c3; (void)o4;
+    (void)pstride; (void)pbase;
 }
 
 // synthetic candle panel for the bench (device-side, counter-based): a random walk of opens with bodies and

@@ -300,10 +300,10 @@ void release_schema(ArrowSchema *s) {
     s->release = nullptr;
 }
 
-void export_schema(ArrowSchema *s, const char *name, int n_fields, const char *const *field_names) {
+void export_schema(ArrowSchema *s, const char *name, int n_fields, const char *const *field_names, const char *prim = "g") {
     SchemaPriv *p = new SchemaPriv{name, {}};
     memset(s, 0, sizeof(*s));
-    s->format = n_fields ? "+s" : "g";
+    s->format = n_fields ? "+s" : prim;
     s->name = p->name.c_str();
     s->flags = 2;                                             // ARROW_FLAG_NULLABLE
     for (int i = 0; i < n_fields; ++i) {
@@ -497,6 +497,131 @@ bool call_impl(int fn, pqb_series_export *in, size_t n_in, const uint8_t *kw, si
     return true;
 }
 
+// ---- candle functions: cdl* (Int32) and the price transforms / bop -----------------------------------
+struct I32Priv { int32_t *vals; const void *bufs[2]; };
+
+void release_i32(ArrowArray *a) {
+    if (!a || !a->release) return;
+    I32Priv *p = static_cast<I32Priv *>(a->private_data);
+    free(p->vals);
+    delete p;
+    a->release = nullptr;
+}
+
+void finish_series(pqb_series_export *ret, ArrowArray *arr, ArrowSchema *field) {
+    SeriesPriv *pr = new SeriesPriv{field, new ArrowArray *[1]{arr}};
+    ret->field = field;
+    ret->arrays = pr->arrays;
+    ret->len = 1;
+    ret->release = release_series;
+    ret->private_data = pr;
+}
+
+// pattern.rs:9 `#[polars_expr(output_type=Int32)] pub fn cdl2crows(inputs)`: open, high, low, close (+ an optional
+// Float64 `penetration` literal, `inputs.get(4)`); the Series is named after the function (`from_slice("cdl2crows"...)`)
+bool cdl_impl(int pattern, pqb_series_export *in, size_t n_in, pqb_series_export *ret) {
+    const char *name = pqb_pattern_name(pattern);
+    if (!in || n_in < 4) { set_err("%s: expected 4 input columns (open, high, low, close), got %zu", name, n_in); return false; }
+    if (!ret) { set_err("%s: NULL return_value", name); return false; }
+    double pen = 0.3;
+    if (n_in > 4) literal_value(&in[4], &pen);
+    Column cols[4];
+    for (int i = 0; i < 4; ++i)
+        if (!import_column(&in[i], i, &cols[i])) return false;
+    const int64_t n = cols[0].col.len;
+    for (int i = 1; i < 4; ++i)
+        if (cols[i].col.len != n) { set_err("%s: input columns differ in length", name); return false; }
+    void *buf = nullptr;
+    if (posix_memalign(&buf, 64, (size_t)((std::max<int64_t>(n, 1) * 4 + 63) / 64 * 64))) { set_err("out of memory"); return false; }
+    memset(buf, 0, (size_t)std::max<int64_t>(n, 1) * 4);
+    if (n > 0) {
+        pqb_engine *e = engine();
+        int rc = e ? pqb_cdl(e, pattern, &cols[0].col, &cols[1].col, &cols[2].col, &cols[3].col, pen, static_cast<int32_t *>(buf))
+                   : PQB_ERR_NO_DEVICE;
+        if (rc != PQB_OK) {
+            if (e) set_err("%s: %s", name, pqb_last_error());
+            free(buf);
+            return false;
+        }
+    } else {
+        // the reference refuses nulls even in an empty column? cont_slice() of an empty array is fine: nothing to do
+    }
+    I32Priv *p = new I32Priv{static_cast<int32_t *>(buf), {nullptr, buf}};
+    ArrowArray *arr = new ArrowArray;
+    memset(arr, 0, sizeof(*arr));
+    arr->length = n;
+    arr->n_buffers = 2;
+    arr->buffers = p->bufs;
+    arr->release = release_i32;
+    arr->private_data = p;
+    ArrowSchema *field = new ArrowSchema;
+    export_schema(field, name, 0, nullptr, "i");
+    finish_series(ret, arr, field);
+    return true;
+}
+
+// price.rs:10-91 avgprice(open, high, low, close) medprice(high, low) typprice / wclprice(high, low, close);
+// momentum.rs:113 bop(open, high, low, close)
+bool price_impl(int which, pqb_series_export *in, size_t n_in, pqb_series_export *ret) {
+    static const char *const names[5] = {"avgprice", "medprice", "typprice", "wclprice", "bop"};
+    static const int n_cols[5] = {4, 2, 3, 3, 4};
+    static const int slot[5][4] = {{0, 1, 2, 3}, {1, 2, -1, -1}, {1, 2, 3, -1}, {1, 2, 3, -1}, {0, 1, 2, 3}};   // -> o, h, l, c
+    const char *name = names[which];
+    if (!in || n_in < (size_t)n_cols[which]) { set_err("%s: expected %d input columns, got %zu", name, n_cols[which], n_in); return false; }
+    if (!ret) { set_err("%s: NULL return_value", name); return false; }
+    Column cols[4];
+    const pqb_col *ohlc[4] = {nullptr, nullptr, nullptr, nullptr};
+    int64_t n = -1;
+    for (int i = 0; i < n_cols[which]; ++i) {
+        if (!import_column(&in[i], i, &cols[i])) return false;
+        if (n >= 0 && cols[i].col.len != n) { set_err("%s: input columns differ in length", name); return false; }
+        n = cols[i].col.len;
+        ohlc[slot[which][i]] = &cols[i].col;
+    }
+    OutCol out;
+    if (!alloc_out(n, &out)) return false;
+    if (n > 0) {
+        pqb_engine *e = engine();
+        pqb_out_col o{out.vals, out.valid};
+        int rc = e ? pqb_price(e, which, ohlc[0], ohlc[1], ohlc[2], ohlc[3], &o) : PQB_ERR_NO_DEVICE;
+        if (rc != PQB_OK) {
+            if (e) set_err("%s: %s", name, pqb_last_error());
+            free(out.vals);
+            free(out.valid);
+            return false;
+        }
+    }
+    ArrowArray *arr = new ArrowArray;
+    export_prim(out, arr);
+    ArrowSchema *field = new ArrowSchema;
+    export_schema(field, name, 0, nullptr);
+    finish_series(ret, arr, field);
+    return true;
+}
+
+template <class F>
+void guarded(const char *name, pqb_series_export *in, size_t n_in, F &&f) {
+    g_perr.clear();
+    try {
+        f();
+    } catch (const std::exception &ex) {
+        set_err("%s: %s", name, ex.what());
+    } catch (...) {
+        set_err("%s: unknown C++ exception", name);
+    }
+    if (in) release_inputs(in, n_in);
+}
+
+void typed_field(ArrowSchema *fields, size_t n, ArrowSchema *out, const char *fmt) {       // FieldsMapper::with_dtype
+    g_perr.clear();
+    if (!out) return;
+    try {
+        export_schema(out, (fields && n && fields[0].name) ? fields[0].name : "", 0, nullptr, fmt);
+    } catch (...) {
+        set_err("cannot build the output field");
+    }
+}
+
 void plugin_call(int fn, pqb_series_export *in, size_t n_in, const uint8_t *kw, size_t kwl, pqb_series_export *ret) {
     g_perr.clear();
     bool ok = false;
@@ -560,3 +685,26 @@ PQB_DEFINE_PLUGIN(ad, F_AD)
 PQB_DEFINE_PLUGIN(adosc, F_ADOSC)
 PQB_DEFINE_PLUGIN(stoch, F_STOCH)
 PQB_DEFINE_PLUGIN(kdj, F_KDJ)
+
+// ---- candle symbols: the 61 cdl* functions (pattern.rs) in the reference's order, price.rs, bop ---------
+#define PQB_DEFINE_CDL(name, id)                                                                               \
+    extern "C" void _polars_plugin_##name(pqb_series_export *in, size_t n, const uint8_t *, size_t,            \
+                                          pqb_series_export *ret, void *) {                                    \
+        guarded(#name, in, n, [&] { cdl_impl(id, in, n, ret); });                                              \
+    }                                                                                                          \
+    extern "C" void _polars_plugin_field_##name(ArrowSchema *f, size_t n, ArrowSchema *out) { typed_field(f, n, out, "i"); }
+#define PQB_DEFINE_PRICE(name, id)                                                                             \
+    extern "C" void _polars_plugin_##name(pqb_series_export *in, size_t n, const uint8_t *, size_t,            \
+                                          pqb_series_export *ret, void *) {                                    \
+        guarded(#name, in, n, [&] { price_impl(id, in, n, ret); });                                            \
+    }                                                                                                          \
+    extern "C" void _polars_plugin_field_##name(ArrowSchema *f, size_t n, ArrowSchema *out) { typed_field(f, n, out, "g"); }
+
+#define X(n) PQB_DEFINE_CDL(n, pqb_pattern_index(#n))
+PQB_CDL_LIST(X)
+#undef X
+PQB_DEFINE_PRICE(avgprice, PQB_PRICE_AVG)
+PQB_DEFINE_PRICE(medprice, PQB_PRICE_MED)
+PQB_DEFINE_PRICE(typprice, PQB_PRICE_TYP)
+PQB_DEFINE_PRICE(wclprice, PQB_PRICE_WCL)
+PQB_DEFINE_PRICE(bop, PQB_PRICE_BOP)

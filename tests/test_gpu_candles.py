@@ -137,3 +137,30 @@ def test_large_panel_properties():
     avg, ok = p.price(0)
     assert ok.all() and np.array_equal(avg, (o + h + l + c) * 0.25)
     p.close()
+
+
+def test_candle_functions_through_the_polars_plugin_symbols(g):
+    import pyarrow as pa
+    from polars_quant_b200 import plugin
+    names = [str(n) for n in g["names"]]
+    s = 11
+    cols = [pa.array(g[k][s]) for k in ("open", "high", "low", "close")]
+    for n in ("cdl3inside", "cdlengulfing", "cdlkicking", "cdlxsidegap3methods", "cdlshortline"):
+        out = plugin.call(n, cols)
+        assert out.type == pa.int32() and out.null_count == 0
+        assert np.array_equal(out.to_numpy(), g["patterns"][names.index(n)][s]), n
+    j = [str(x) for x in g["penetration_names"]].index("cdleveningstar")
+    out = plugin.call("cdleveningstar", cols + [float(g["penetration_value"])])
+    assert np.array_equal(out.to_numpy(), g["patterns_pen"][j][s])
+    o, h, l, c = cols
+    for n, args, k in (("avgprice", [o, h, l, c], 0), ("medprice", [h, l], 1), ("typprice", [h, l, c], 2),
+                       ("wclprice", [h, l, c], 3), ("bop", [o, h, l, c], 4)):
+        out = plugin.call(n, args)
+        assert out.null_count == 0 and np.array_equal(out.to_numpy().view(np.uint64), g["prices"][k][s].view(np.uint64)), n
+    hn = pa.array(g["high"][s], mask=np.arange(g["high"].shape[1]) == 7)
+    out = plugin.call("typprice", [hn, l, c])
+    assert out.null_count == 1 and not out[7].is_valid                  # price.rs:66-69 null-propagating
+    with pytest.raises(plugin.PluginError, match="not contiguous"):
+        plugin.call("cdldoji", [o, hn, l, c])                           # pattern.rs:14 cont_slice()?
+    with pytest.raises(plugin.PluginError, match="not contiguous"):
+        plugin.call("bop", [o, hn, l, c])                               # momentum.rs:119

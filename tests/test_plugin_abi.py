@@ -43,6 +43,25 @@ def test_every_declared_plugin_symbol_is_exported(plugin):
     assert plugin.version() == (0, 1)
 
 
+def test_candle_plugin_symbols(plugin):
+    from polars_quant_b200 import _native as N, candles
+    L = N.lib()
+    names = candles.pattern_names() + ["avgprice", "medprice", "typprice", "wclprice", "bop"]
+    assert len(names) == 66
+    for n in names:
+        assert hasattr(L, "_polars_plugin_" + n) and hasattr(L, "_polars_plugin_field_" + n), n
+    ins = [pa.field(x, pa.float64()) for x in ("o", "h", "l", "c")]
+    f = plugin.output_field("cdlengulfing", ins)
+    assert f.name == "o" and f.type == pa.int32()                      # #[polars_expr(output_type=Int32)] pattern.rs:9
+    assert plugin.output_field("bop", ins).type == pa.float64()
+    e = pa.array([], type=pa.float64())
+    out = plugin.call("cdlhammer", [e, e, e, e])
+    assert out.type == pa.int32() and len(out) == 0
+    assert plugin.call("medprice", [e, e]).type == pa.float64()
+    with pytest.raises(plugin.PluginError, match="expected 4 input columns"):
+        plugin.call("cdldoji", [e, e])
+
+
 def test_field_functions_return_the_reference_output_fields(plugin):
     f = plugin.output_field("ema", [pa.field("AAPL_close", pa.float64()), pa.field("literal", pa.int32())])
     assert f.name == "AAPL_close" and f.type == pa.float64()          # FieldsMapper::with_dtype(Float64)
