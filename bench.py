@@ -195,6 +195,7 @@ def main():
     ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
     ap.add_argument("--symbols", type=int, default=0, help="override symbols per GPU")
     ap.add_argument("--bars", type=int, default=0)
+    ap.add_argument("--no-extra", action="store_true", help="skip the kernel-only lines of the other shapes (config 2, candles)")
     ap.add_argument("--e2e-symbols", type=int, default=8192, help="symbols of the workload pushed through the host path")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
@@ -290,6 +291,36 @@ def main():
     else:
         cpu = None
 
+    # ---- the other measured shapes of BASELINE.json / SURVEY.md 8f, kernel-only, reported beside the headline
+    #      (N=1 only; a few seconds): config 2 on the same suite kernel, and the fused candle kernel ----
+    other = None
+    if world == 1 and not args.no_extra:
+        other = {}
+        try:
+            panel.close()
+            if (S, N) != WORKLOADS["c2"][:2]:
+                S2, N2, d2 = WORKLOADS["c2"]
+                p2 = pq.Panel(S2, N2, engine=engine, host_staging=False)
+                p2.fill_synthetic(seed=0xC0FFEE, sigma=0.02)
+                _, f2, _ = p2.time_device(params, warmup=3, iters=20)
+                p2.close()
+                g2 = ALGO_BYTES_PER_SYMBOL_BAR * S2 * N2 / (f2 / 20 * 1e-3) / 1e9
+                other["c2"] = {"workload": d2, "kernel": "suite_fused_kernel<true,false>", "kernel_ms": f2 / 20,
+                               "value": S2 * N2 / (f2 / 20 * 1e-3), "unit": UNIT, "achieved_gbs": g2, "frac": g2 / peak}
+            from polars_quant_b200 import candles
+            Sc, Nc = 20_000, 5_040
+            cp = candles.CandlePanel(Sc, Nc, engine=engine, host_staging=False)
+            cp.fill_random_walk(seed=0xC0FFEE, sigma=0.02)
+            msc = cp.time_device(warmup=3, iters=10) / 10
+            cp.close()
+            gc = 316 * Sc * Nc / (msc * 1e-3) / 1e9
+            other["candles"] = {"workload": "SURVEY 8f.1: 61 cdl* patterns + 4 price transforms + bop, 20,000 x 5,040 random-walk OHLC",
+                                "kernel": "candle_kernel<true>", "kernel_ms": msc, "value": Sc * Nc / (msc * 1e-3),
+                                "unit": "symbol*bars/s", "algorithmic_bytes_per_symbol_bar": 316, "achieved_gbs": gc,
+                                "frac": gc / peak}
+        except Exception as ex:          # never lose the headline line to an extra
+            other["error"] = repr(ex)
+
     if rank == 0:
         traffic = None
         tp = ROOT / "profiles" / "traffic.json"
@@ -317,6 +348,8 @@ def main():
             "gpu_launches": launches * args.steps + e2e_launches,
             "clocks": clocks.summary(),
         }
+        if other:
+            line["other_workloads"] = other
         print(json.dumps(line), flush=True)
     panel.close()
     if dist is not None:

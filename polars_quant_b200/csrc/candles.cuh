@@ -112,7 +112,7 @@ __device__ __forceinline__ void st_i32(int32_t *p, int v) { __stcs(p, v); }
 // grid = (ceil(n_bars / CANDLE_TILE), symbols of this launch), CANDLE_TILE threads.
 // ALL: every pattern enabled and the 61 planes are one allocation (no mask tests, one base pointer).
 template <bool ALL>
-__global__ void __launch_bounds__(CANDLE_TILE) candle_kernel(const __grid_constant__ CandleArgs A, const uint64_t pmask) {
+__global__ void __launch_bounds__(CANDLE_TILE, 3) candle_kernel(const __grid_constant__ CandleArgs A, const uint64_t pmask) {
     __shared__ double so[CANDLE_TILE + CANDLE_HALO], sh[CANDLE_TILE + CANDLE_HALO], sl[CANDLE_TILE + CANDLE_HALO],
         sc[CANDLE_TILE + CANDLE_HALO];
     __shared__ unsigned short sf[CANDLE_TILE + CANDLE_HALO];
