@@ -127,6 +127,21 @@ def lib() -> C.CDLL:
         L.pqb_panel_tiled_shape.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
         L.pqb_suite_params_default.argtypes = [C.POINTER(SuiteParams)]
         L.pqb_suite_params_default.restype = None
+        # time-split panels
+        L.pqb_split_required_warmup.argtypes = [C.POINTER(SuiteParams)]
+        L.pqb_split_required_warmup.restype = C.c_int64
+        L.pqb_split_create.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_uint32, C.c_uint32, C.c_int,
+                                       C.POINTER(C.c_void_p)]
+        L.pqb_split_destroy.argtypes = [C.c_void_p]
+        L.pqb_split_destroy.restype = None
+        L.pqb_split_panel.argtypes = [C.c_void_p]
+        L.pqb_split_panel.restype = C.c_void_p
+        L.pqb_split_shape.argtypes = [C.c_void_p] + [C.POINTER(C.c_int64)] * 4
+        L.pqb_split_set_column.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64]
+        L.pqb_split_run.argtypes = [C.c_void_p, C.POINTER(SuiteParams)]
+        L.pqb_split_run_host.argtypes = [C.c_void_p, C.POINTER(SuiteParams)]
+        L.pqb_split_get_output.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_int64]
+        L.pqb_split_fill_synthetic.argtypes = [C.c_void_p, C.c_uint64, C.c_double]
         # candle engine
         L.pqb_candle_params_default.argtypes = [C.POINTER(CandleParams)]
         L.pqb_candle_params_default.restype = None

@@ -1469,3 +1469,4 @@ extern "C" int pqb_multi_run_host(pqb_multi *m, const pqb_suite_params *params) 
 }
 
 #include "candles_host.inc"
+#include "split_host.inc"

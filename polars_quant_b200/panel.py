@@ -179,6 +179,72 @@ class Panel:
         return tot.value
 
 
+class SplitPanel:
+    """Long rows, few symbols (BASELINE config 3): every row runs as `chunks` independent virtual symbols, each with
+    `warmup` bars of real history in front (include/pqb200.h "time-split panels").  Chunk 0 is bit-exact; later
+    chunks agree with the serial computation to < 1e-12 relative when warmup >= required_warmup(params)."""
+
+    def __init__(self, n_symbols: int, n_bars: int, chunks: int, warmup: int, engine: Engine | None = None,
+                 fields_mask: int = 0xF, outputs_mask: int = (1 << N.N_SUITE_OUTPUTS) - 1, host_staging: bool = True):
+        self.engine = engine or get_engine(0)
+        self.n_symbols, self.n_bars = int(n_symbols), int(n_bars)
+        self.outputs_mask = outputs_mask
+        self._h = C.c_void_p()
+        N.check(N.lib().pqb_split_create(self.engine._h, n_symbols, n_bars, chunks, warmup, fields_mask, outputs_mask,
+                                         1 if host_staging else 0, C.byref(self._h)))
+        a, b, c, d = (C.c_int64() for _ in range(4))
+        N.check(N.lib().pqb_split_shape(self._h, C.byref(a), C.byref(b), C.byref(c), C.byref(d)))
+        self.chunk_bars, self.warmup, self.virtual_symbols, self.virtual_bars = a.value, b.value, c.value, d.value
+
+    @staticmethod
+    def required_warmup(params: N.SuiteParams) -> int:
+        return int(N.lib().pqb_split_required_warmup(C.byref(params)))
+
+    def close(self):
+        if self._h:
+            N.lib().pqb_split_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_column(self, symbol: int, field, values: np.ndarray):
+        f = Panel.FIELDS[field] if isinstance(field, str) else int(field)
+        v = np.ascontiguousarray(values, dtype=np.float64)
+        N.check(N.lib().pqb_split_set_column(self._h, symbol, f, v.ctypes.data_as(C.c_void_p), None, 0, v.size))
+
+    def set_fields(self, close=None, high=None, low=None, volume=None):
+        for f, a in ((N.CLOSE, close), (N.HIGH, high), (N.LOW, low), (N.VOLUME, volume)):
+            if a is not None:
+                for s in range(self.n_symbols):
+                    self.set_column(s, f, a[s])
+
+    def run_host(self, params: N.SuiteParams | None = None):
+        params = params or N.default_params()
+        N.check(N.lib().pqb_split_run_host(self._h, C.byref(params)))
+
+    def get_output(self, symbol: int, k: int):
+        v = np.empty(self.n_bars, dtype=np.float64)
+        bits = np.zeros((self.n_bars + 7) // 8, dtype=np.uint8)
+        N.check(N.lib().pqb_split_get_output(self._h, symbol, k, v.ctypes.data_as(C.c_void_p), bits.ctypes.data_as(C.c_void_p),
+                                             self.n_bars))
+        return v, np.unpackbits(bits, bitorder="little")[:self.n_bars].astype(bool)
+
+    def fill_synthetic(self, seed: int = 0xC0FFEE, sigma: float = 0.0005):
+        N.check(N.lib().pqb_split_fill_synthetic(self._h, seed, sigma))
+
+    def time_device(self, params=None, warmup: int = 2, iters: int = 5):
+        """(total ms, fused-kernel ms, launches per step) of `iters` passes over the device-resident virtual panel."""
+        params = params or N.default_params()
+        tot, fused, nl = C.c_float(), C.c_float(), C.c_int()
+        inner = N.lib().pqb_split_panel(self._h)
+        N.check(N.lib().pqb_suite_time(inner, C.byref(params), warmup, iters, C.byref(tot), C.byref(fused), C.byref(nl)))
+        return tot.value, fused.value, nl.value
+
+
 class MultiPanel:
     """Multi-GPU driver (pqb_multi_*): one shard = engine + panel per listed device, symbols split in
     contiguous whole-block ranges, one host thread per shard, no collective."""

@@ -68,3 +68,19 @@ def test_product_never_imports_the_oracle():
     for f in (ROOT / "polars_quant_b200").rglob("*"):
         if f.suffix in (".py", ".cu", ".cuh", ".h") and f.is_file():
             assert "oracle" not in f.read_text().replace("the oracle", "").replace("oracle's", ""), f
+
+
+def test_split_required_warmup_rules(lib):
+    import ctypes as C
+    from polars_quant_b200 import _native as N
+    w = lambda **kw: lib.pqb_split_required_warmup(C.byref(N.default_params(**kw)))
+    assert w() == -1                                                    # OBV / AD never forget
+    assert w(indicators=N.IND["obv"]) == -1 and w(indicators=N.IND_EXTRA["midpoint"]) == -1
+    assert w(indicators=N.IND["sma"]) == -1 and w(indicators=N.IND["bbands"]) == -1 and w(indicators=N.IND["kdj"]) == -1
+    assert w(indicators=N.IND["willr"], willr_period=14) == 32          # a window: its own length, rounded to 32
+    e = w(indicators=N.IND["ema"], ema_period=5000)
+    assert e % 32 == 0 and 5000 + 14 * 5001 <= e < 5000 + 14 * 5001 + 32
+    a = 2.0 / 5001.0
+    assert (1.0 - a) ** (e - 5000) < 1e-12                              # the seed error is forgotten below the tolerance
+    assert w(indicators=N.IND["rsi"], rsi_period=14) >= 29 * 14
+    assert (1.0 - 1.0 / 14) ** (29 * 14 - 14) < 1e-12
