@@ -123,6 +123,15 @@ PQB_POLARS_PLUGIN(adosc)     /* :34   (high, low, close, volume; fastperiod=3, s
 PQB_POLARS_PLUGIN(stoch)     /* (high, low, close; fastk_period=5, slowk_period=3, slowd_period=3) -> struct stoch{slowk, slowd} */
 PQB_POLARS_PLUGIN(kdj)       /* (high, low, close; fastk_period=9, k_period=3, d_period=3) -> struct kdj{k, d, j} */
 
+/* the directional-movement family, momentum.rs; all (…; timeperiod=14) */
+PQB_POLARS_PLUGIN(adx)       /* :11   (high, low, close) */
+PQB_POLARS_PLUGIN(adxr)      /* :29   (high, low, close) */
+PQB_POLARS_PLUGIN(dx)        /* :226  (high, low, close) */
+PQB_POLARS_PLUGIN(plus_di)   /* :401  (high, low, close) -- returns calc_dm().0, i.e. DX, like the reference */
+PQB_POLARS_PLUGIN(minus_di)  /* :346  (high, low, close) */
+PQB_POLARS_PLUGIN(plus_dm)   /* :418  (high, low) */
+PQB_POLARS_PLUGIN(minus_dm)  /* :362  (high, low) */
+
 /* candle functions: pattern.rs:9-2065 `#[polars_expr(output_type=Int32)] pub fn cdl*(inputs)`
  * (open, high, low, close [, penetration Float64 literal]) -> Int32 in {-100, 0, 100}, in the reference's order of
  * definition = pattern ids 0..60 of pqb200.h; price.rs:10-91 and momentum.rs:113 (bop) -> Float64 */

@@ -499,6 +499,54 @@ EXPORT int pqo_adosc(const double *h, const uint8_t *hok, const double *l, const
     return PQO_OK;
 }
 
+/* ------------------------------------------------------------------ calc_dm and the DM / DI / DX / ADX family
+ * momentum.rs:668-727 (calc_dm), :11-61 (adx, adxr), :226-237 (dx), :344-436 (minus_di, minus_dm, plus_di,
+ * plus_dm) + D1 (calc_rma).  p_dm[0] = m_dm[0] = tr[0] = 0; the three Wilder averages; DI = 100 * S / ST, null
+ * where ST == 0; dx = 100 |p - m| / (p + m) (0 where the sum is 0).  calc_dm returns (dx, minus_di): the
+ * reference's `plus_di` takes `.0`, i.e. it returns DX (:409) -- restated literally: out_plus_di == dx.
+ * adx = calc_rma(dx with None -> 0.0); adxr[i] = (adx[i] + adx[i - (p-1)]) * 0.5 from i = p-1.
+ * Nulls in any input: cont_slice()? -> error. */
+EXPORT int pqo_dm(const double *h, const uint8_t *hok, const double *l, const uint8_t *lok, const double *c,
+                  const uint8_t *cok, int64_t n, int64_t p,
+                  double *plus_dm, uint8_t *plus_dm_ok, double *minus_dm, uint8_t *minus_dm_ok,
+                  double *dx, uint8_t *dx_ok, double *minus_di, uint8_t *minus_di_ok,
+                  double *adx, uint8_t *adx_ok, double *adxr, uint8_t *adxr_ok) {
+    if (has_nulls(hok, n) || has_nulls(lok, n) || has_nulls(cok, n)) return PQO_ERR_NULLS;
+    double *pd = (double *)calloc((size_t)(n + 1), sizeof(double)), *md = (double *)calloc((size_t)(n + 1), sizeof(double));
+    double *tr = (double *)calloc((size_t)(n + 1), sizeof(double)), *st = (double *)malloc(sizeof(double) * (size_t)(n + 1));
+    double *dx0 = (double *)calloc((size_t)(n + 1), sizeof(double));
+    uint8_t *stok = (uint8_t *)malloc((size_t)(n + 1));
+    if (!pd || !md || !tr || !st || !dx0 || !stok) { free(pd); free(md); free(tr); free(st); free(dx0); free(stok); return PQO_ERR_ALLOC; }
+    for (int64_t i = 1; i < n; ++i) {                                                   /* :680-699 */
+        double up_move = h[i] - h[i - 1], down_move = l[i - 1] - l[i];
+        if (up_move > down_move && up_move > 0.0) pd[i] = up_move;
+        if (down_move > up_move && down_move > 0.0) md[i] = down_move;
+        tr[i] = rs_max(rs_max(h[i] - l[i], fabs(h[i] - c[i - 1])), fabs(l[i] - c[i - 1]));
+    }
+    pqo_rma(pd, n, p, plus_dm, plus_dm_ok);                                            /* :701-703; also plus_dm :418-435 */
+    pqo_rma(md, n, p, minus_dm, minus_dm_ok);
+    pqo_rma(tr, n, p, st, stok);
+    for (int64_t i = 0; i < n; ++i) {                                                   /* :705-725 */
+        if (plus_dm_ok[i] && minus_dm_ok[i] && stok[i] && st[i] != 0.0) {
+            double p_di = 100.0 * plus_dm[i] / st[i], m_di = 100.0 * minus_dm[i] / st[i];
+            put_val(minus_di, minus_di_ok, i, m_di);
+            double diff = fabs(p_di - m_di), sum = p_di + m_di;
+            double d = (sum == 0.0) ? 0.0 : 100.0 * diff / sum;
+            put_val(dx, dx_ok, i, d);
+            dx0[i] = d;
+        } else { put_null(minus_di, minus_di_ok, i); put_null(dx, dx_ok, i); }
+    }
+    pqo_rma(dx0, n, p, adx, adx_ok);                                                    /* :20-26 */
+    for (int64_t i = 0; i < n; ++i) put_null(adxr, adxr_ok, i);
+    if (p >= 1)
+        for (int64_t i = p - 1; i < n; ++i) {                                           /* :49-57 */
+            int64_t j = i - (p - 1);                                                    /* saturating_sub: i >= p-1 here */
+            if (adx_ok[i] && adx_ok[j]) put_val(adxr, adxr_ok, i, (adx[i] + adx[j]) * 0.5);
+        }
+    free(pd); free(md); free(tr); free(st); free(dx0); free(stok);
+    return PQO_OK;
+}
+
 /* ------------------------------------------------------------------ willr
  * momentum.rs:630-662.  Brute-force window, f64::MIN/MAX init, Rust max/min. */
 EXPORT int pqo_willr(const double *h, const uint8_t *hok, const double *l, const uint8_t *lok,

@@ -191,6 +191,12 @@ def kdj(h, l, c, fastk=9, k=3, d=3):
     return _call("pqo_kdj", [_col(h), _col(l), _col(c)], [fastk, k, d], 3)
 
 
+def dm(h, l, c, p=14):
+    """-> dict plus_dm, minus_dm, dx (== the reference's plus_di), minus_di, adx, adxr: (values, ok) each."""
+    res = _call("pqo_dm", [_col(h), _col(l), _col(c)], [p], 6)
+    return dict(zip(("plus_dm", "minus_dm", "dx", "minus_di", "adx", "adxr"), res))
+
+
 def donchian(h, l, p=20):
     h, _ = _col(h)
     l, _ = _col(l)

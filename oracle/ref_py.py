@@ -366,6 +366,56 @@ def willr(high, low, close, timeperiod=14):  # momentum.rs:630-662
     return res
 
 
+def calc_dm(high, low, close, timeperiod):  # momentum.rs:668-727 -> (dx, minus_di)
+    n = len(high)
+    p_dm, m_dm, tr = [0.0] * n, [0.0] * n, [0.0] * n
+    for i in range(1, n):
+        up_move = high[i] - high[i - 1]
+        down_move = low[i - 1] - low[i]
+        if up_move > down_move and up_move > 0.0:
+            p_dm[i] = up_move
+        if down_move > up_move and down_move > 0.0:
+            m_dm[i] = down_move
+        tr[i] = rs_max(rs_max(high[i] - low[i], abs(high[i] - close[i - 1])), abs(low[i] - close[i - 1]))
+    sp, sm, st = calc_rma(p_dm, timeperiod), calc_rma(m_dm, timeperiod), calc_rma(tr, timeperiod)
+    plus_di, minus_di = [None] * n, [None] * n
+    for i in range(n):
+        if sp[i] is not None and sm[i] is not None and st[i] is not None and st[i] != 0.0:
+            plus_di[i] = 100.0 * sp[i] / st[i]
+            minus_di[i] = 100.0 * sm[i] / st[i]
+    dx = [None] * n
+    for i in range(n):
+        if plus_di[i] is not None and minus_di[i] is not None:
+            diff, sm_ = abs(plus_di[i] - minus_di[i]), plus_di[i] + minus_di[i]
+            dx[i] = 0.0 if sm_ == 0.0 else 100.0 * diff / sm_
+    return dx, minus_di
+
+
+def dm_family(high, low, close, timeperiod=14):
+    """plus_dm :418, minus_dm :362, plus_di :401 (returns calc_dm().0 == DX), minus_di :346, dx :226, adx :11,
+    adxr :29 -- as a dict of columns."""
+    _cont_slice(high, low, close)
+    n = len(high)
+    p_dm, m_dm = [0.0] * n, [0.0] * n
+    for i in range(1, n):
+        up_move = high[i] - high[i - 1]
+        down_move = low[i - 1] - low[i]
+        if up_move > down_move and up_move > 0.0:
+            p_dm[i] = up_move
+        if down_move > up_move and down_move > 0.0:
+            m_dm[i] = down_move
+    dx, minus_di = calc_dm(high, low, close, timeperiod)
+    adx = calc_rma([0.0 if v is None else v for v in dx], timeperiod)
+    adxr = [None] * n
+    if timeperiod >= 1:
+        for i in range(timeperiod - 1, n):
+            prev = adx[max(0, i - (timeperiod - 1))]
+            if adx[i] is not None and prev is not None:
+                adxr[i] = (adx[i] + prev) * 0.5
+    return {"plus_dm": calc_rma(p_dm, timeperiod), "minus_dm": calc_rma(m_dm, timeperiod), "plus_di": dx, "dx": dx,
+            "minus_di": minus_di, "adx": adx, "adxr": adxr}
+
+
 def mom(real, timeperiod=10):  # momentum.rs:384-397
     _cont_slice(real)
     n = len(real)

@@ -71,7 +71,7 @@ extern "C" void pqb_suite_params_default(pqb_suite_params *p) {
     p->kdj_fastk = 9; p->kdj_slowk = 3; p->kdj_slowd = 3;
     p->willr_period = 14; p->midprice_period = 14;
     p->midpoint_period = 14; p->adosc_fast = 3; p->adosc_slow = 10; p->mom_period = 10; p->roc_period = 10;
-    p->cmo_period = 14; p->mfi_period = 14; p->cci_period = 14;
+    p->cmo_period = 14; p->mfi_period = 14; p->cci_period = 14; p->dm_period = 14;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -99,7 +99,8 @@ struct pqb_panel {
     int64_t n_symbols = 0, n_bars = 0, pitch = 0, words_per_row = 0;
     int64_t n_blocks = 0, bars_padded = 0;   // tiled geometry
     size_t plane_doubles = 0;            // n_blocks * bars_padded * 32
-    uint32_t fields_mask = 0, outputs_mask = 0;
+    uint32_t fields_mask = 0;
+    uint64_t outputs_mask = 0;
     double *d_in[PQB_N_FIELDS] = {};     // tiled
     double *d_out[PQB_N_OUTPUTS] = {};   // tiled
     uint32_t *d_bits[PQB_N_OUTPUTS] = {};// row-major bitmaps
@@ -183,12 +184,12 @@ extern "C" void pqb_engine_destroy(pqb_engine *e) {
 }
 
 extern "C" int pqb_panel_create(pqb_engine *e, int64_t n_symbols, int64_t n_bars, uint32_t fields_mask,
-                                uint32_t outputs_mask, int host_staging, pqb_panel **out) {
+                                uint64_t outputs_mask, int host_staging, pqb_panel **out) {
     if (!e || !out) return fail(PQB_ERR_INVALID, "pqb_panel_create: NULL argument");
     *out = nullptr;
     if (n_symbols <= 0 || n_bars <= 0 || n_symbols > (1ll << 30) || n_bars > (1ll << 30))
         return fail(PQB_ERR_INVALID, "pqb_panel_create: bad shape %lld x %lld", (long long)n_symbols, (long long)n_bars);
-    if (fields_mask == 0 || fields_mask >= (1u << PQB_N_FIELDS) || outputs_mask >= (1u << PQB_N_OUTPUTS))
+    if (fields_mask == 0 || fields_mask >= (1u << PQB_N_FIELDS) || outputs_mask >= (1ull << PQB_N_OUTPUTS))
         return fail(PQB_ERR_INVALID, "pqb_panel_create: bad masks");
     int rc = set_dev(e);
     if (rc) return rc;
@@ -707,6 +708,12 @@ static int build_args(const pqb_panel *p, const pqb_suite_params *sp, Built *out
         else { A.gmask |= G_CCI; A.cci_p = sp->cci_period; A.cci_pd = (double)sp->cci_period; A.inv_cci = 1.0 / (double)sp->cci_period;
                bind_dyn(PQB_OUT_CCI); upto(sp->cci_period); }
     }
+    if (ind & PQB_IND_DM) {
+        if (sp->dm_period <= 0) { for (int k = PQB_OUT_PLUS_DM; k <= PQB_OUT_ADXR; ++k) null_only(k); }   // calc_rma guard (D1)
+        else { A.gmask |= G_DM; A.dm_p = sp->dm_period; A.a_dm = 1.0 / (double)sp->dm_period;              // D1: alpha = 1/p
+               for (int k = PQB_OUT_PLUS_DM; k <= PQB_OUT_ADXR; ++k) bind_dyn(k);
+               upto(2ll * sp->dm_period); }
+    }
     for (int k = PQB_N_SUITE_OUTPUTS; k < PQB_N_OUTPUTS; ++k)
         if (A.out[k] && !p->d_ovm[k]) return fail(PQB_ERR_INVALID, "internal: validity words of output %d are not allocated", k);
     A.steady_lead = steady;
@@ -716,7 +723,7 @@ static int build_args(const pqb_panel *p, const pqb_suite_params *sp, Built *out
     for (int r = 0; r < N_ROLES; ++r)
         if (A.gmask & ROLE_GROUPS[r]) { A.roles |= 1u << r; ++A.n_roles; }
     if (A.gmask & ~(unsigned)G_MIDPRICE) A.fields |= F_C;                     // everything but midprice reads close
-    if (A.gmask & (G_TRANGE | G_ATR | G_NATR | G_AD | G_KDJ | G_WILLR | G_MIDPRICE | G_ADOSC | G_MFI | G_CCI)) A.fields |= F_H | F_L;
+    if (A.gmask & (G_TRANGE | G_ATR | G_NATR | G_AD | G_KDJ | G_WILLR | G_MIDPRICE | G_ADOSC | G_MFI | G_CCI | G_DM)) A.fields |= F_H | F_L;
     if (A.gmask & (G_OBV | G_AD | G_ADOSC | G_MFI)) A.fields |= F_V;
 
     // shared-memory rings (slots of 32 doubles)
@@ -741,6 +748,7 @@ static int build_args(const pqb_panel *p, const pqb_suite_params *sp, Built *out
     A.off_mfip = take((A.gmask & G_MFI) ? A.mfi_p : 0); A.off_mfin = take((A.gmask & G_MFI) ? A.mfi_p : 0);
     A.off_cci = take((A.gmask & G_CCI) ? A.cci_p : 0);
     A.off_mph = take((A.gmask & G_MIDPOINT) ? A.midpoint_p + 1 : 0); A.off_mpl = take((A.gmask & G_MIDPOINT) ? A.midpoint_p + 1 : 0);
+    A.off_adx = take((A.gmask & G_DM) ? A.dm_p - 1 : 0);
     const long long smem = (long long)kFixedSmem + off * 8;
     if (smem > kMaxSmem)
         return fail(PQB_ERR_UNSUPPORTED,
@@ -761,8 +769,8 @@ __global__ void nan_fill_kernel(double *p, size_t n) {
 }
 
 // which outputs does an enabled group actually store?  (used for the period-0 NaN fill)
-static uint32_t outputs_of_groups(unsigned g) {
-    uint32_t m = 0;
+static uint64_t outputs_of_groups(unsigned g) {
+    uint64_t m = 0;
     if (g & G_SMA) m |= 1u << 0;
     if (g & G_EMA) m |= 1u << 1;
     if (g & G_TEMA) m |= 1u << 2;
@@ -785,6 +793,7 @@ static uint32_t outputs_of_groups(unsigned g) {
     if (g & G_CMO) m |= 1u << 28;
     if (g & G_MFI) m |= 1u << 29;
     if (g & G_CCI) m |= 1u << 30;
+    if (g & G_DM) m |= 0x3full << 31;
     return m;
 }
 
@@ -793,7 +802,7 @@ static int launch_suite(pqb_panel *p, const Built &full, int64_t b0, int64_t nb,
                         int *launches) {
     pqb_engine *e = p->e;
     int n_launch = 0;
-    const uint32_t stored = outputs_of_groups(full.a.gmask);
+    const uint64_t stored = outputs_of_groups(full.a.gmask);
     const size_t boff = (size_t)b0 * p->bars_padded * SYM, bn = (size_t)nb * p->bars_padded * SYM;
     for (int k = 0; k < PQB_N_OUTPUTS; ++k) {
         if (full.a.out[k] && !(stored >> k & 1)) {
@@ -1189,7 +1198,7 @@ static int run_single(pqb_engine *e, const pqb_col *const *cols, const int *fiel
     std::lock_guard<std::mutex> lock(e->mu);
     if (!e->scratch || e->scratch_bars != n) {
         if (e->scratch) { pqb_panel_destroy(e->scratch); e->scratch = nullptr; }
-        rc = pqb_panel_create(e, 1, n, (1u << PQB_N_FIELDS) - 1, (1u << PQB_N_OUTPUTS) - 1, 1, &e->scratch);
+        rc = pqb_panel_create(e, 1, n, (1u << PQB_N_FIELDS) - 1, (1ull << PQB_N_OUTPUTS) - 1, 1, &e->scratch);
         if (rc) return rc;
         e->scratch_bars = n;
     }
@@ -1370,6 +1379,22 @@ extern "C" int pqb_cci(pqb_engine *e, const pqb_col *h, const pqb_col *l, const 
     return run_single(e, c, f, 3, NP_ERR, &sp, o, d, 1);
 }
 
+extern "C" int pqb_dm(pqb_engine *e, const pqb_col *h, const pqb_col *l, const pqb_col *cl, int32_t tp, pqb_out_col *plus_dm,
+                      pqb_out_col *minus_dm, pqb_out_col *dx, pqb_out_col *minus_di, pqb_out_col *adx, pqb_out_col *adxr) {
+    pqb_suite_params sp = only(PQB_IND_DM); sp.dm_period = tp;
+    if (!h || !l) return fail(PQB_ERR_INVALID, "pqb_dm: high and low are required");
+    const bool need_close = dx || minus_di || adx || adxr;
+    if (need_close && !cl) return fail(PQB_ERR_INVALID, "pqb_dm: dx / minus_di / adx / adxr need close");
+    // plus_dm / minus_dm alone (momentum.rs:362, :418) read high and low only: a stand-in close keeps the launch uniform
+    const pqb_col *c[] = {h, l, cl ? cl : h}; const int f[] = {PQB_HIGH, PQB_LOW, PQB_CLOSE};
+    pqb_out_col *all[] = {plus_dm, minus_dm, dx, minus_di, adx, adxr};
+    int o[6]; pqb_out_col *d[6]; int n = 0;
+    for (int k = 0; k < 6; ++k)
+        if (all[k]) { o[n] = PQB_OUT_PLUS_DM + k; d[n] = all[k]; ++n; }
+    if (n == 0) return fail(PQB_ERR_INVALID, "pqb_dm: no output requested");
+    return run_single(e, c, f, 3, NP_ERR, &sp, o, d, n);
+}
+
 // ---------------------------------------------------------------------------------------
 // multi-GPU driver: symbol shards, one host thread per shard, no collective
 // ---------------------------------------------------------------------------------------
@@ -1389,7 +1414,7 @@ extern "C" void pqb_multi_destroy(pqb_multi *m) {
 }
 
 extern "C" int pqb_multi_create(const int *devices, int n_devices, int64_t n_symbols, int64_t n_bars,
-                                uint32_t fields_mask, uint32_t outputs_mask, pqb_multi **out) {
+                                uint32_t fields_mask, uint64_t outputs_mask, pqb_multi **out) {
     if (!devices || n_devices <= 0 || !out) return fail(PQB_ERR_INVALID, "pqb_multi_create: bad argument");
     *out = nullptr;
     if (n_symbols <= 0 || n_bars <= 0) return fail(PQB_ERR_INVALID, "pqb_multi_create: bad shape");

@@ -345,7 +345,7 @@ struct Spec {
 
 enum Fn { F_SMA, F_EMA, F_TEMA, F_TRIMA, F_MA, F_BBANDS, F_MIDPOINT, F_MIDPRICE, F_RSI, F_MACD, F_WILLR, F_MOM,
           F_ROC, F_ROCP, F_ROCR, F_ROCR100, F_CMO, F_MFI, F_CCI, F_TRANGE, F_ATR, F_NATR, F_OBV, F_AD, F_ADOSC,
-          F_STOCH, F_KDJ, F_COUNT };
+          F_STOCH, F_KDJ, F_ADX, F_ADXR, F_DX, F_PLUS_DI, F_MINUS_DI, F_PLUS_DM, F_MINUS_DM, F_COUNT };
 
 const Spec SPECS[F_COUNT] = {
     {"sma", 1, 1, {"timeperiod"}, {30}, 1, nullptr, {}},
@@ -375,6 +375,13 @@ const Spec SPECS[F_COUNT] = {
     {"adosc", 4, 2, {"fastperiod", "slowperiod"}, {3, 10}, 1, nullptr, {}},
     {"stoch", 3, 3, {"fastk_period", "slowk_period", "slowd_period"}, {5, 3, 3}, 2, "stoch", {"slowk", "slowd"}},
     {"kdj", 3, 3, {"fastk_period", "k_period", "d_period"}, {9, 3, 3}, 3, "kdj", {"k", "d", "j"}},
+    {"adx", 3, 1, {"timeperiod"}, {14}, 1, nullptr, {}},
+    {"adxr", 3, 1, {"timeperiod"}, {14}, 1, nullptr, {}},
+    {"dx", 3, 1, {"timeperiod"}, {14}, 1, nullptr, {}},
+    {"plus_di", 3, 1, {"timeperiod"}, {14}, 1, nullptr, {}},
+    {"minus_di", 3, 1, {"timeperiod"}, {14}, 1, nullptr, {}},
+    {"plus_dm", 2, 1, {"timeperiod"}, {14}, 1, nullptr, {}},
+    {"minus_dm", 2, 1, {"timeperiod"}, {14}, 1, nullptr, {}},
 };
 
 int run_fn(int fn, pqb_engine *e, const pqb_col *c, const double *pv, pqb_out_col *o) {
@@ -407,6 +414,14 @@ int run_fn(int fn, pqb_engine *e, const pqb_col *c, const double *pv, pqb_out_co
         case F_ADOSC: return pqb_adosc(e, &c[0], &c[1], &c[2], &c[3], p0, p1, &o[0]);
         case F_STOCH: return pqb_stoch(e, &c[0], &c[1], &c[2], p0, p1, p2, &o[0], &o[1]);
         case F_KDJ: return pqb_kdj(e, &c[0], &c[1], &c[2], p0, p1, p2, &o[0], &o[1], &o[2]);
+        // the directional-movement family: one fused call, one requested output (momentum.rs:11-61, 226-237, 344-436)
+        case F_ADX: return pqb_dm(e, &c[0], &c[1], &c[2], p0, nullptr, nullptr, nullptr, nullptr, &o[0], nullptr);
+        case F_ADXR: return pqb_dm(e, &c[0], &c[1], &c[2], p0, nullptr, nullptr, nullptr, nullptr, nullptr, &o[0]);
+        case F_DX: return pqb_dm(e, &c[0], &c[1], &c[2], p0, nullptr, nullptr, &o[0], nullptr, nullptr, nullptr);
+        case F_PLUS_DI: return pqb_dm(e, &c[0], &c[1], &c[2], p0, nullptr, nullptr, &o[0], nullptr, nullptr, nullptr);   // :409 returns calc_dm().0 = DX
+        case F_MINUS_DI: return pqb_dm(e, &c[0], &c[1], &c[2], p0, nullptr, nullptr, nullptr, &o[0], nullptr, nullptr);
+        case F_PLUS_DM: return pqb_dm(e, &c[0], &c[1], nullptr, p0, &o[0], nullptr, nullptr, nullptr, nullptr, nullptr);
+        case F_MINUS_DM: return pqb_dm(e, &c[0], &c[1], nullptr, p0, nullptr, &o[0], nullptr, nullptr, nullptr, nullptr);
     }
     return PQB_ERR_INVALID;
 }
@@ -685,6 +700,13 @@ PQB_DEFINE_PLUGIN(ad, F_AD)
 PQB_DEFINE_PLUGIN(adosc, F_ADOSC)
 PQB_DEFINE_PLUGIN(stoch, F_STOCH)
 PQB_DEFINE_PLUGIN(kdj, F_KDJ)
+PQB_DEFINE_PLUGIN(adx, F_ADX)
+PQB_DEFINE_PLUGIN(adxr, F_ADXR)
+PQB_DEFINE_PLUGIN(dx, F_DX)
+PQB_DEFINE_PLUGIN(plus_di, F_PLUS_DI)
+PQB_DEFINE_PLUGIN(minus_di, F_MINUS_DI)
+PQB_DEFINE_PLUGIN(plus_dm, F_PLUS_DM)
+PQB_DEFINE_PLUGIN(minus_dm, F_MINUS_DM)
 
 // ---- candle symbols: the 61 cdl* functions (pattern.rs) in the reference's order, price.rs, bop ---------
 #define PQB_DEFINE_CDL(name, id)                                                                               \

@@ -255,7 +255,7 @@ class MultiPanel:
         devs = (C.c_int * len(devices))(*devices)
         self._h = C.c_void_p()
         N.check(N.lib().pqb_multi_create(devs, len(devices), C.c_int64(n_symbols), C.c_int64(n_bars),
-                                         C.c_uint32(fields_mask), C.c_uint32(outputs_mask), C.byref(self._h)))
+                                         C.c_uint32(fields_mask), C.c_uint64(outputs_mask), C.byref(self._h)))
 
     def close(self):
         if self._h:

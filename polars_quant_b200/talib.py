@@ -146,6 +146,41 @@ def CCI(high, low, close, timeperiod: int = 14):
     return _call("cci", [high, low, close], [timeperiod])
 
 
+def ADX(high, low, close, timeperiod: int = 14):
+    """ADX - Average Directional Movement Index (momentum.rs:11)"""
+    return _call("adx", [high, low, close], [timeperiod])
+
+
+def ADXR(high, low, close, timeperiod: int = 14):
+    """ADXR - Average Directional Movement Index Rating (momentum.rs:29)"""
+    return _call("adxr", [high, low, close], [timeperiod])
+
+
+def DX(high, low, close, timeperiod: int = 14):
+    """DX - Directional Movement Index (momentum.rs:226)"""
+    return _call("dx", [high, low, close], [timeperiod])
+
+
+def PLUS_DI(high, low, close, timeperiod: int = 14):
+    """PLUS_DI - Plus Directional Indicator (momentum.rs:401; the reference returns calc_dm().0, i.e. DX)"""
+    return _call("plus_di", [high, low, close], [timeperiod])
+
+
+def MINUS_DI(high, low, close, timeperiod: int = 14):
+    """MINUS_DI - Minus Directional Indicator (momentum.rs:346)"""
+    return _call("minus_di", [high, low, close], [timeperiod])
+
+
+def PLUS_DM(high, low, timeperiod: int = 14):
+    """PLUS_DM - Plus Directional Movement (momentum.rs:418)"""
+    return _call("plus_dm", [high, low], [timeperiod])
+
+
+def MINUS_DM(high, low, timeperiod: int = 14):
+    """MINUS_DM - Minus Directional Movement (momentum.rs:362)"""
+    return _call("minus_dm", [high, low], [timeperiod])
+
+
 def STOCH(high, low, close, fastk_period: int = 5, slowk_period: int = 3, slowk_matype: int = 0,
           slowd_period: int = 3, slowd_matype: int = 0):
     """STOCH - Stochastic (SlowK, SlowD).  The reference composes it in Python from polars rolling
@@ -195,4 +230,4 @@ def ADOSC(high, low, close, volume, fastperiod: int = 3, slowperiod: int = 10):
 
 __all__ = ["SMA", "EMA", "TEMA", "TRIMA", "MA", "BBANDS", "MIDPOINT", "MIDPRICE", "RSI", "MACD", "MACDFIX", "WILLR",
            "MOM", "ROC", "ROCP", "ROCR", "ROCR100", "CMO", "MFI", "CCI", "STOCH", "KDJ", "TRANGE", "ATR", "NATR",
-           "OBV", "AD", "ADOSC"]
+           "OBV", "AD", "ADOSC", "ADX", "ADXR", "DX", "PLUS_DI", "MINUS_DI", "PLUS_DM", "MINUS_DM"]

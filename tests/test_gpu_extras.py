@@ -13,12 +13,16 @@ pytestmark = pytest.mark.gpu
 
 import tolerances as T
 
-EXTRA_OUT = ("midpoint", "adosc", "mom", "roc", "rocp", "rocr", "rocr100", "cmo", "mfi", "cci")
+EXTRA_OUT = ("midpoint", "adosc", "mom", "roc", "rocp", "rocr", "rocr100", "cmo", "mfi", "cci",
+             "plus_dm", "minus_dm", "dx", "minus_di", "adx", "adxr")
+DM_OUT = ("plus_dm", "minus_dm", "dx", "minus_di", "adx", "adxr")
 
 
 def _refs(d, s, P):
     c, h, l, v = (d[f][s] for f in ("close", "high", "low", "volume"))
+    dm = pqo.dm(h, l, c, P.get("dm_period", 14))             # calc_dm family, momentum.rs:668-727
     return {
+        **dm,
         "midpoint": pqo.midpoint(c, P["midpoint_period"]),
         "adosc": pqo.adosc(h, l, c, v, P["adosc_fast"], P["adosc_slow"]),
         "mom": pqo.mom(c, P["mom_period"]),
@@ -42,14 +46,14 @@ def _data():
 
 
 @pytest.mark.parametrize("periods", [dict(), dict(midpoint_period=5, adosc_fast=2, adosc_slow=7, mom_period=1, roc_period=3,
-                                                  cmo_period=1, mfi_period=2, cci_period=1),
+                                                  cmo_period=1, mfi_period=2, cci_period=1, dm_period=1),
                                      dict(midpoint_period=60, adosc_fast=30, adosc_slow=12, mom_period=55, roc_period=41,
-                                          cmo_period=33, mfi_period=29, cci_period=47)])
+                                          cmo_period=33, mfi_period=29, cci_period=47, dm_period=37)])
 def test_optional_groups_alone_and_with_the_suite(periods):
     import polars_quant_b200 as pq
     from polars_quant_b200 import _native as N
     P = dict(midpoint_period=14, adosc_fast=3, adosc_slow=10, mom_period=10, roc_period=10, cmo_period=14,
-             mfi_period=14, cci_period=14)
+             mfi_period=14, cci_period=14, dm_period=14)
     P.update(periods)
     d = _data()
     S, NB = d["close"].shape
@@ -69,7 +73,7 @@ def test_optional_groups_alone_and_with_the_suite(periods):
     # one group at a time
     for g, bit in N.IND_EXTRA.items():
         res = panel.compute(N.default_params(indicators=bit, **P))
-        names = ("roc", "rocp", "rocr", "rocr100") if g == "roc" else (g,)
+        names = ("roc", "rocp", "rocr", "rocr100") if g == "roc" else DM_OUT if g == "dm" else (g,)
         for s in (0, 5, 6, 7, 8, 36):
             refs = _refs(d, s, P)
             for name in names:
@@ -85,7 +89,7 @@ def test_optional_groups_with_leading_nulls_and_host_pipeline():
     S, NB = d["close"].shape
     starts = np.random.default_rng(4).integers(0, 120, S).astype(np.int32)
     P = dict(midpoint_period=14, adosc_fast=3, adosc_slow=10, mom_period=10, roc_period=10, cmo_period=14,
-             mfi_period=14, cci_period=14)
+             mfi_period=14, cci_period=14, dm_period=14)
     panel = pq.Panel(S, NB, outputs_mask=(1 << N.N_OUTPUTS) - 1)
     panel.set_fields(d["close"], d["high"], d["low"], d["volume"], starts=starts)
     panel.run_host(N.default_params(indicators=sum(N.IND_EXTRA.values()) | N.IND_ALL), chunk_symbols=32)
@@ -127,3 +131,38 @@ def test_optional_single_column_entry_points():
     assert T.compare("mfi", *got(), *pqo.mfi(h, l, c, v, 14))[0] == 0
     N.check(L.pqb_cci(eng._h, C.byref(ch), C.byref(cl), C.byref(cc), 14, C.byref(oc)))
     assert T.compare("cci", *got(), *pqo.cci(h, l, c, 14))[0] == 0
+
+
+def test_directional_movement_family_quirks_and_plugin_names():
+    """calc_dm family (momentum.rs:668-727): flat bars (smoothed true range 0 -> DI / DX null, ADX keeps smoothing
+    zeros), the reference's plus_di == DX quirk (:409), first valid bars p-1 / 2p-2, nulls refused, period 0."""
+    import pyarrow as pa
+    import polars_quant_b200 as pq
+    from polars_quant_b200 import _native as N
+    from polars_quant_b200 import plugin, talib
+    d = synth.ohlcv(1, 400, seed=77)
+    h, l, c = d["high"][0].copy(), d["low"][0].copy(), d["close"][0].copy()
+    h[:40] = l[:40] = c[:40] = 50.0                           # a flat listing period: true range 0 for 40 bars
+    ref = pqo.dm(h, l, c, 14)
+    assert not ref["dx"][1][13:30].any() and ref["adx"][1][13] and ref["adx"][0][20] == 0.0
+    ah, al, ac = pa.array(h), pa.array(l), pa.array(c)
+
+    def same(name, got, r):
+        ok = ~np.asarray(got.is_null())
+        v = np.where(ok, np.asarray(got.to_numpy(zero_copy_only=False), dtype=np.float64), np.nan)
+        nbad, msg = T.compare(name, v, ok, r[0], r[1])
+        assert nbad == 0, msg
+
+    same("adx", talib.ADX(ah, al, ac), ref["adx"])
+    same("adxr", talib.ADXR(ah, al, ac, 14), ref["adxr"])
+    same("dx", talib.DX(ah, al, ac), ref["dx"])
+    same("plus_di == dx", talib.PLUS_DI(ah, al, ac), ref["dx"])
+    same("minus_di", talib.MINUS_DI(ah, al, ac), ref["minus_di"])
+    same("plus_dm", talib.PLUS_DM(ah, al), ref["plus_dm"])
+    same("minus_dm", talib.MINUS_DM(ah, al, 14), ref["minus_dm"])
+    r5 = pqo.dm(h, l, c, 5)
+    same("adxr(5)", plugin.call("adxr", [ah, al, ac], kwargs={"timeperiod": 5}), r5["adxr"])
+    assert int(np.argmax(r5["adx"][1])) == 4 and int(np.argmax(r5["adxr"][1])) == 8
+    assert talib.ADX(ah, al, ac, 0).null_count == 400         # calc_rma guard (D1)
+    with pytest.raises(plugin.PluginError, match="not contiguous"):
+        talib.ADX(pa.array(h, mask=np.arange(400) == 100), al, ac)

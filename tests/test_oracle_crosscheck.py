@@ -36,6 +36,11 @@ def test_random_columns(seed):
     _eq(pqo.trange(h, l, c, okp, okp, okp), R.calc_trange(ho, lo, co), "trange")
     _eq(pqo.atr(h, l, c, p, okp, okp, okp), R.atr(ho, lo, co, p), "atr")
     _eq(pqo.natr(h, l, c, p, okp, okp, okp), R.natr(ho, lo, co, p), "natr")
+    if okp is None:                                            # calc_dm family: cont_slice()? refuses nulls
+        dm_c, dm_p = pqo.dm(h, l, c, p), R.dm_family(ho, lo, co, p)
+        for k in ("plus_dm", "minus_dm", "dx", "minus_di", "adx", "adxr"):
+            _eq(dm_c[k], dm_p[k], "dm." + k)
+        _eq(dm_c["dx"], dm_p["plus_di"], "plus_di == dx (momentum.rs:409)")
     _eq(pqo.obv(c, v, okp, okp), R.obv(co, vo), "obv")
     _eq(pqo.ad(h, l, c, v, okp, okp, okp, okp), R.calc_ad(ho, lo, co, vo), "ad")
     _eq(pqo.adosc(h, l, c, v, 3, 10, okp, okp, okp, okp), R.adosc(ho, lo, co, vo, 3, 10), "adosc")
