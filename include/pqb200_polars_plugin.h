@@ -131,6 +131,9 @@ PQB_POLARS_PLUGIN(plus_di)   /* :401  (high, low, close) -- returns calc_dm().0,
 PQB_POLARS_PLUGIN(minus_di)  /* :346  (high, low, close) */
 PQB_POLARS_PLUGIN(plus_dm)   /* :418  (high, low) */
 PQB_POLARS_PLUGIN(minus_dm)  /* :362  (high, low) */
+PQB_POLARS_PLUGIN(trix)      /* :544  (real; timeperiod=30) */
+PQB_POLARS_PLUGIN(ultosc)    /* :573  (high, low, close; timeperiod1=7, timeperiod2=14, timeperiod3=28) */
+PQB_POLARS_PLUGIN(aroon)     /* :63   (high, low; timeperiod=14) -> struct aroon{aroon_up, aroon_down} */
 
 /* candle functions: pattern.rs:9-2065 `#[polars_expr(output_type=Int32)] pub fn cdl*(inputs)`
  * (open, high, low, close [, penetration Float64 literal]) -> Int32 in {-100, 0, 100}, in the reference's order of

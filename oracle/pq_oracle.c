@@ -33,6 +33,7 @@
  *  D3 KDJ := STOCH(high, low, close, 9, 3, 0, 3, 0) per momentum.py:178-186,
  *     K = slowk, D = slowd, J = 3*K - 2*D (null where K or D null).
  */
+#include <float.h>
 #include <math.h>
 #include <stdint.h>
 #include <stdlib.h>
@@ -544,6 +545,81 @@ EXPORT int pqo_dm(const double *h, const uint8_t *hok, const double *l, const ui
             if (adx_ok[i] && adx_ok[j]) put_val(adxr, adxr_ok, i, (adx[i] + adx[j]) * 0.5);
         }
     free(pd); free(md); free(tr); free(st); free(dx0); free(stok);
+    return PQO_OK;
+}
+
+/* ------------------------------------------------------------------ trix
+ * momentum.rs:544-571 (+ D2 slice-style calc_ema).  ema2 / ema3 run over the WHOLE previous array with
+ * None -> 0.0, so all three seed at index p-1; res[i] = (e3[i] - e3[i-1]) / e3[i-1] * 100, null where e3[i-1] == 0. */
+EXPORT int pqo_trix(const double *x, const uint8_t *xok, int64_t n, int64_t p, double *out, uint8_t *ok) {
+    if (has_nulls(xok, n)) return PQO_ERR_NULLS;
+    double *e = (double *)malloc(sizeof(double) * (size_t)(3 * n + 3)), *z = (double *)malloc(sizeof(double) * (size_t)(n + 1));
+    uint8_t *k = (uint8_t *)malloc((size_t)(3 * n + 3));
+    if (!e || !z || !k) { free(e); free(z); free(k); return PQO_ERR_ALLOC; }
+    double *e1 = e, *e2 = e + n, *e3 = e + 2 * n; uint8_t *k1 = k, *k2 = k + n, *k3 = k + 2 * n;
+    pqo_ema(x, NULL, n, p, e1, k1);
+    for (int64_t i = 0; i < n; ++i) z[i] = k1[i] ? e1[i] : 0.0;
+    pqo_ema(z, NULL, n, p, e2, k2);
+    for (int64_t i = 0; i < n; ++i) z[i] = k2[i] ? e2[i] : 0.0;
+    pqo_ema(z, NULL, n, p, e3, k3);
+    for (int64_t i = 0; i < n; ++i) put_null(out, ok, i);
+    for (int64_t i = 1; i < n; ++i)
+        if (k3[i] && k3[i - 1] && e3[i - 1] != 0.0) put_val(out, ok, i, (e3[i] - e3[i - 1]) / e3[i - 1] * 100.0);
+    free(e); free(z); free(k);
+    return PQO_OK;
+}
+
+/* ------------------------------------------------------------------ ultosc
+ * momentum.rs:573-627.  bp[0] = tr[0] = 0; running sums over p1 / p2 / p3 bars (from index 0); an average is
+ * null where its range sum is 0; 100 * (4 a1 + 2 a2 + a3) / 7.  Periods must be >= 1 (usize underflow otherwise). */
+EXPORT int pqo_ultosc(const double *h, const uint8_t *hok, const double *l, const uint8_t *lok, const double *c,
+                      const uint8_t *cok, int64_t n, int64_t p1, int64_t p2, int64_t p3, double *out, uint8_t *ok) {
+    if (has_nulls(hok, n) || has_nulls(lok, n) || has_nulls(cok, n)) return PQO_ERR_NULLS;
+    if (p1 < 1 || p2 < 1 || p3 < 1) return PQO_ERR_SHAPE;
+    double *bp = (double *)calloc((size_t)(n + 1), sizeof(double)), *tr = (double *)calloc((size_t)(n + 1), sizeof(double));
+    double *a = (double *)malloc(sizeof(double) * (size_t)(3 * n + 3));
+    uint8_t *ak = (uint8_t *)calloc((size_t)(3 * n + 3), 1);
+    if (!bp || !tr || !a || !ak) { free(bp); free(tr); free(a); free(ak); return PQO_ERR_ALLOC; }
+    for (int64_t i = 1; i < n; ++i) {
+        double min_l_pc = fmin(l[i], c[i - 1]), max_h_pc = fmax(h[i], c[i - 1]);        /* Rust f64::min / max */
+        bp[i] = c[i] - min_l_pc;
+        tr[i] = max_h_pc - min_l_pc;
+    }
+    const int64_t per[3] = {p1, p2, p3};
+    for (int q = 0; q < 3; ++q) {                                                       /* fn avg :598-613 */
+        double s_bp = 0.0, s_tr = 0.0; const int64_t p = per[q];
+        for (int64_t i = 0; i < n; ++i) {
+            s_bp += bp[i]; s_tr += tr[i];
+            if (i >= p) { s_bp -= bp[i - p]; s_tr -= tr[i - p]; }
+            if (i >= p - 1 && s_tr != 0.0) { a[q * n + i] = s_bp / s_tr; ak[q * n + i] = 1; }
+        }
+    }
+    for (int64_t i = 0; i < n; ++i) {
+        if (ak[i] && ak[n + i] && ak[2 * n + i]) put_val(out, ok, i, 100.0 * (4.0 * a[i] + 2.0 * a[n + i] + a[2 * n + i]) / 7.0);
+        else put_null(out, ok, i);
+    }
+    free(bp); free(tr); free(a); free(ak);
+    return PQO_OK;
+}
+
+/* ------------------------------------------------------------------ aroon
+ * momentum.rs:63-110.  For i >= p: last position of the maximum of high / minimum of low (`>=` / `<=` scans from
+ * f64::MIN / f64::MAX) in the p+1 bars [i-p, i], divided by p, times 100.  p must be >= 1. */
+EXPORT int pqo_aroon(const double *h, const uint8_t *hok, const double *l, const uint8_t *lok, int64_t n, int64_t p,
+                     double *up, uint8_t *upok, double *down, uint8_t *downok) {
+    if (has_nulls(hok, n) || has_nulls(lok, n)) return PQO_ERR_NULLS;
+    if (p < 1) return PQO_ERR_SHAPE;
+    for (int64_t i = 0; i < n; ++i) { put_null(up, upok, i); put_null(down, downok, i); }
+    for (int64_t i = p; i < n; ++i) {
+        int64_t start = i - p, max_idx = 0, min_idx = 0;
+        double max_val = -DBL_MAX, min_val = DBL_MAX;
+        for (int64_t j = start; j <= i; ++j) {
+            if (h[j] >= max_val) { max_val = h[j]; max_idx = j - start; }
+            if (l[j] <= min_val) { min_val = l[j]; min_idx = j - start; }
+        }
+        put_val(up, upok, i, ((double)max_idx / (double)p) * 100.0);
+        put_val(down, downok, i, ((double)min_idx / (double)p) * 100.0);
+    }
     return PQO_OK;
 }
 

@@ -197,6 +197,18 @@ def dm(h, l, c, p=14):
     return dict(zip(("plus_dm", "minus_dm", "dx", "minus_di", "adx", "adxr"), res))
 
 
+def trix(x, p=30, ok=None): return _call("pqo_trix", [_col(x, ok)], [p], 1)
+
+
+def ultosc(h, l, c, p1=7, p2=14, p3=28):
+    return _call("pqo_ultosc", [_col(h), _col(l), _col(c)], [p1, p2, p3], 1)
+
+
+def aroon(h, l, p=14):
+    """-> ((aroon_up, ok), (aroon_down, ok))"""
+    return _call("pqo_aroon", [_col(h), _col(l)], [p], 2)
+
+
 def donchian(h, l, p=20):
     h, _ = _col(h)
     l, _ = _col(l)

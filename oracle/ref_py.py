@@ -416,6 +416,68 @@ def dm_family(high, low, close, timeperiod=14):
             "minus_di": minus_di, "adx": adx, "adxr": adxr}
 
 
+def _slice_ema(x, timeperiod):  # D2: calc_ema over a plain slice (the no-validity branch overlap.rs:705-724)
+    return calc_ema(list(x), timeperiod)
+
+
+def trix(real, timeperiod=30):  # momentum.rs:544-571
+    _cont_slice(real)
+    e1 = _slice_ema(real, timeperiod)
+    e2 = _slice_ema([0.0 if v is None else v for v in e1], timeperiod)
+    e3 = _slice_ema([0.0 if v is None else v for v in e2], timeperiod)
+    n = len(e3)
+    res = [None] * n
+    for i in range(1, n):
+        curr, prev = e3[i], e3[i - 1]
+        if curr is not None and prev is not None and prev != 0.0:
+            res[i] = (curr - prev) / prev * 100.0
+    return res
+
+
+def ultosc(high, low, close, p1=7, p2=14, p3=28):  # momentum.rs:573-627
+    _cont_slice(high, low, close)
+    n = len(high)
+    bp, tr = [0.0] * n, [0.0] * n
+    for i in range(1, n):
+        min_l_pc = rs_min(low[i], close[i - 1])
+        max_h_pc = rs_max(high[i], close[i - 1])
+        bp[i] = close[i] - min_l_pc
+        tr[i] = max_h_pc - min_l_pc
+
+    def avg(p):
+        res, s_bp, s_tr = [None] * n, 0.0, 0.0
+        for i in range(n):
+            s_bp += bp[i]
+            s_tr += tr[i]
+            if i >= p:
+                s_bp -= bp[i - p]
+                s_tr -= tr[i - p]
+            if i >= p - 1 and s_tr != 0.0:
+                res[i] = s_bp / s_tr
+        return res
+
+    a1, a2, a3 = avg(p1), avg(p2), avg(p3)
+    return [None if (a1[i] is None or a2[i] is None or a3[i] is None) else 100.0 * (4.0 * a1[i] + 2.0 * a2[i] + a3[i]) / 7.0
+            for i in range(n)]
+
+
+def aroon(high, low, timeperiod=14):  # momentum.rs:63-110 -> (aroon_up, aroon_down)
+    _cont_slice(high, low)
+    n = len(high)
+    up, down = [None] * n, [None] * n
+    for i in range(timeperiod, n):
+        start = i - timeperiod
+        max_idx, max_val, min_idx, min_val = 0, F64_MIN, 0, F64_MAX
+        for j in range(start, i + 1):
+            if high[j] >= max_val:
+                max_val, max_idx = high[j], j - start
+            if low[j] <= min_val:
+                min_val, min_idx = low[j], j - start
+        up[i] = (float(max_idx) / float(timeperiod)) * 100.0
+        down[i] = (float(min_idx) / float(timeperiod)) * 100.0
+    return up, down
+
+
 def mom(real, timeperiod=10):  # momentum.rs:384-397
     _cont_slice(real)
     n = len(real)

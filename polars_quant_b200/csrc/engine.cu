@@ -72,6 +72,7 @@ extern "C" void pqb_suite_params_default(pqb_suite_params *p) {
     p->willr_period = 14; p->midprice_period = 14;
     p->midpoint_period = 14; p->adosc_fast = 3; p->adosc_slow = 10; p->mom_period = 10; p->roc_period = 10;
     p->cmo_period = 14; p->mfi_period = 14; p->cci_period = 14; p->dm_period = 14;
+    p->trix_period = 30; p->ultosc_period1 = 7; p->ultosc_period2 = 14; p->ultosc_period3 = 28; p->aroon_period = 14;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -165,6 +166,8 @@ extern "C" int pqb_engine_create(int device, pqb_engine **out) {
     CU(cudaFuncSetAttribute(suite_fused_kernel<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     CU(cudaFuncSetAttribute(suite_fused_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
     CU(cudaFuncSetAttribute(suite_fused_kernel<false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    CU(cudaFuncSetAttribute(suite_fused_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+    CU(cudaFuncSetAttribute(suite_fused_kernel<false, false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     CU(cudaFuncSetAttribute(suite_fused_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
     CU(cudaFuncSetAttribute(suite_fused_kernel<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     *out = e;
@@ -714,6 +717,22 @@ static int build_args(const pqb_panel *p, const pqb_suite_params *sp, Built *out
                for (int k = PQB_OUT_PLUS_DM; k <= PQB_OUT_ADXR; ++k) bind_dyn(k);
                upto(2ll * sp->dm_period); }
     }
+    if (ind & PQB_IND_TRIX) {
+        if (sp->trix_period <= 0) { null_only(PQB_OUT_TRIX); }                                            // calc_ema guard
+        else { A.gmask |= G_TRIX; A.trix_p = sp->trix_period; A.a_trix = ema_alpha(sp->trix_period);
+               bind_dyn(PQB_OUT_TRIX); upto((long long)sp->trix_period + 1); }
+    }
+    if (ind & PQB_IND_ULTOSC) {
+        if (sp->ultosc_period1 <= 0 || sp->ultosc_period2 <= 0 || sp->ultosc_period3 <= 0)
+            return fail(PQB_ERR_UNSUPPORTED, "ultosc with a period <= 0 (usize underflow in the reference) is not built");
+        A.gmask |= G_ULTOSC; A.ult_p1 = sp->ultosc_period1; A.ult_p2 = sp->ultosc_period2; A.ult_p3 = sp->ultosc_period3;
+        bind_dyn(PQB_OUT_ULTOSC); upto((long long)std::max(std::max(A.ult_p1, A.ult_p2), A.ult_p3) + 1);
+    }
+    if (ind & PQB_IND_AROON) {
+        if (sp->aroon_period <= 0) return fail(PQB_ERR_UNSUPPORTED, "aroon period %d <= 0 (0 / 0 in the reference) is not built", sp->aroon_period);
+        A.gmask |= G_AROON; A.aroon_p = sp->aroon_period; A.aroon_pd = (double)sp->aroon_period;
+        bind_dyn(PQB_OUT_AROON_UP); bind_dyn(PQB_OUT_AROON_DOWN); upto((long long)sp->aroon_period + 1);
+    }
     for (int k = PQB_N_SUITE_OUTPUTS; k < PQB_N_OUTPUTS; ++k)
         if (A.out[k] && !p->d_ovm[k]) return fail(PQB_ERR_INVALID, "internal: validity words of output %d are not allocated", k);
     A.steady_lead = steady;
@@ -723,7 +742,7 @@ static int build_args(const pqb_panel *p, const pqb_suite_params *sp, Built *out
     for (int r = 0; r < N_ROLES; ++r)
         if (A.gmask & ROLE_GROUPS[r]) { A.roles |= 1u << r; ++A.n_roles; }
     if (A.gmask & ~(unsigned)G_MIDPRICE) A.fields |= F_C;                     // everything but midprice reads close
-    if (A.gmask & (G_TRANGE | G_ATR | G_NATR | G_AD | G_KDJ | G_WILLR | G_MIDPRICE | G_ADOSC | G_MFI | G_CCI | G_DM)) A.fields |= F_H | F_L;
+    if (A.gmask & (G_TRANGE | G_ATR | G_NATR | G_AD | G_KDJ | G_WILLR | G_MIDPRICE | G_ADOSC | G_MFI | G_CCI | G_DM | G_ULTOSC | G_AROON)) A.fields |= F_H | F_L;
     if (A.gmask & (G_OBV | G_AD | G_ADOSC | G_MFI)) A.fields |= F_V;
 
     // shared-memory rings (slots of 32 doubles)
@@ -749,6 +768,8 @@ static int build_args(const pqb_panel *p, const pqb_suite_params *sp, Built *out
     A.off_cci = take((A.gmask & G_CCI) ? A.cci_p : 0);
     A.off_mph = take((A.gmask & G_MIDPOINT) ? A.midpoint_p + 1 : 0); A.off_mpl = take((A.gmask & G_MIDPOINT) ? A.midpoint_p + 1 : 0);
     A.off_adx = take((A.gmask & G_DM) ? A.dm_p - 1 : 0);
+    A.off_ult = take((A.gmask & G_ULTOSC) ? 2 * std::max(std::max(A.ult_p1, A.ult_p2), A.ult_p3) : 2);
+    A.off_arh = take((A.gmask & G_AROON) ? A.aroon_p + 1 : 0); A.off_arl = take((A.gmask & G_AROON) ? A.aroon_p + 1 : 0);
     const long long smem = (long long)kFixedSmem + off * 8;
     if (smem > kMaxSmem)
         return fail(PQB_ERR_UNSUPPORTED,
@@ -794,6 +815,9 @@ static uint64_t outputs_of_groups(unsigned g) {
     if (g & G_MFI) m |= 1u << 29;
     if (g & G_CCI) m |= 1u << 30;
     if (g & G_DM) m |= 0x3full << 31;
+    if (g & G_TRIX) m |= 1ull << 37;
+    if (g & G_ULTOSC) m |= 1ull << 38;
+    if (g & G_AROON) m |= 3ull << 39;
     return m;
 }
 
@@ -824,6 +848,7 @@ static int launch_suite(pqb_panel *p, const Built &full, int64_t b0, int64_t nb,
         for (int k = 0; k < PQB_N_SUITE_OUTPUTS; ++k) fulls &= a.out[k] != nullptr;
         if (a.vmask) suite_fused_kernel<false, true><<<(unsigned)nb, CTA_THREADS, a.smem_bytes, e->stream>>>(a);
         else if (fulls) suite_fused_kernel<true, false><<<(unsigned)nb, CTA_THREADS, a.smem_bytes, e->stream>>>(a);
+        else if (!(a.gmask & ~(unsigned)G_ALL)) suite_fused_kernel<false, false, true><<<(unsigned)nb, CTA_THREADS, a.smem_bytes, e->stream>>>(a);
         else suite_fused_kernel<false, false><<<(unsigned)nb, CTA_THREADS, a.smem_bytes, e->stream>>>(a);
         CU(cudaGetLastError());
         ++n_launch;
@@ -1379,6 +1404,24 @@ extern "C" int pqb_cci(pqb_engine *e, const pqb_col *h, const pqb_col *l, const 
     return run_single(e, c, f, 3, NP_ERR, &sp, o, d, 1);
 }
 
+extern "C" int pqb_trix(pqb_engine *e, const pqb_col *real, int32_t tp, pqb_out_col *out) {
+    pqb_suite_params sp = only(PQB_IND_TRIX); sp.trix_period = tp;
+    const pqb_col *c[] = {real}; const int f[] = {PQB_CLOSE}; const int o[] = {PQB_OUT_TRIX}; pqb_out_col *d[] = {out};
+    return run_single(e, c, f, 1, NP_ERR, &sp, o, d, 1);
+}
+extern "C" int pqb_ultosc(pqb_engine *e, const pqb_col *h, const pqb_col *l, const pqb_col *cl, int32_t p1, int32_t p2, int32_t p3,
+                          pqb_out_col *out) {
+    pqb_suite_params sp = only(PQB_IND_ULTOSC); sp.ultosc_period1 = p1; sp.ultosc_period2 = p2; sp.ultosc_period3 = p3;
+    const pqb_col *c[] = {h, l, cl}; const int f[] = {PQB_HIGH, PQB_LOW, PQB_CLOSE}; const int o[] = {PQB_OUT_ULTOSC};
+    pqb_out_col *d[] = {out};
+    return run_single(e, c, f, 3, NP_ERR, &sp, o, d, 1);
+}
+extern "C" int pqb_aroon(pqb_engine *e, const pqb_col *h, const pqb_col *l, int32_t tp, pqb_out_col *up, pqb_out_col *down) {
+    pqb_suite_params sp = only(PQB_IND_AROON); sp.aroon_period = tp;
+    const pqb_col *c[] = {h, l}; const int f[] = {PQB_HIGH, PQB_LOW};
+    const int o[] = {PQB_OUT_AROON_UP, PQB_OUT_AROON_DOWN}; pqb_out_col *d[] = {up, down};
+    return run_single(e, c, f, 2, NP_ERR, &sp, o, d, 2);
+}
 extern "C" int pqb_dm(pqb_engine *e, const pqb_col *h, const pqb_col *l, const pqb_col *cl, int32_t tp, pqb_out_col *plus_dm,
                       pqb_out_col *minus_dm, pqb_out_col *dx, pqb_out_col *minus_di, pqb_out_col *adx, pqb_out_col *adxr) {
     pqb_suite_params sp = only(PQB_IND_DM); sp.dm_period = tp;

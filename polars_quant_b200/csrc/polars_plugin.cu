@@ -345,7 +345,7 @@ struct Spec {
 
 enum Fn { F_SMA, F_EMA, F_TEMA, F_TRIMA, F_MA, F_BBANDS, F_MIDPOINT, F_MIDPRICE, F_RSI, F_MACD, F_WILLR, F_MOM,
           F_ROC, F_ROCP, F_ROCR, F_ROCR100, F_CMO, F_MFI, F_CCI, F_TRANGE, F_ATR, F_NATR, F_OBV, F_AD, F_ADOSC,
-          F_STOCH, F_KDJ, F_ADX, F_ADXR, F_DX, F_PLUS_DI, F_MINUS_DI, F_PLUS_DM, F_MINUS_DM, F_COUNT };
+          F_STOCH, F_KDJ, F_ADX, F_ADXR, F_DX, F_PLUS_DI, F_MINUS_DI, F_PLUS_DM, F_MINUS_DM, F_TRIX, F_ULTOSC, F_AROON, F_COUNT };
 
 const Spec SPECS[F_COUNT] = {
     {"sma", 1, 1, {"timeperiod"}, {30}, 1, nullptr, {}},
@@ -382,6 +382,9 @@ const Spec SPECS[F_COUNT] = {
     {"minus_di", 3, 1, {"timeperiod"}, {14}, 1, nullptr, {}},
     {"plus_dm", 2, 1, {"timeperiod"}, {14}, 1, nullptr, {}},
     {"minus_dm", 2, 1, {"timeperiod"}, {14}, 1, nullptr, {}},
+    {"trix", 1, 1, {"timeperiod"}, {30}, 1, nullptr, {}},
+    {"ultosc", 3, 3, {"timeperiod1", "timeperiod2", "timeperiod3"}, {7, 14, 28}, 1, nullptr, {}},
+    {"aroon", 2, 1, {"timeperiod"}, {14}, 2, "aroon", {"aroon_up", "aroon_down"}},
 };
 
 int run_fn(int fn, pqb_engine *e, const pqb_col *c, const double *pv, pqb_out_col *o) {
@@ -422,6 +425,9 @@ int run_fn(int fn, pqb_engine *e, const pqb_col *c, const double *pv, pqb_out_co
         case F_MINUS_DI: return pqb_dm(e, &c[0], &c[1], &c[2], p0, nullptr, nullptr, nullptr, &o[0], nullptr, nullptr);
         case F_PLUS_DM: return pqb_dm(e, &c[0], &c[1], nullptr, p0, &o[0], nullptr, nullptr, nullptr, nullptr, nullptr);
         case F_MINUS_DM: return pqb_dm(e, &c[0], &c[1], nullptr, p0, nullptr, &o[0], nullptr, nullptr, nullptr, nullptr);
+        case F_TRIX: return pqb_trix(e, &c[0], p0, &o[0]);
+        case F_ULTOSC: return pqb_ultosc(e, &c[0], &c[1], &c[2], p0, p1, p2, &o[0]);
+        case F_AROON: return pqb_aroon(e, &c[0], &c[1], p0, &o[0], &o[1]);
     }
     return PQB_ERR_INVALID;
 }
@@ -707,6 +713,9 @@ PQB_DEFINE_PLUGIN(plus_di, F_PLUS_DI)
 PQB_DEFINE_PLUGIN(minus_di, F_MINUS_DI)
 PQB_DEFINE_PLUGIN(plus_dm, F_PLUS_DM)
 PQB_DEFINE_PLUGIN(minus_dm, F_MINUS_DM)
+PQB_DEFINE_PLUGIN(trix, F_TRIX)
+PQB_DEFINE_PLUGIN(ultosc, F_ULTOSC)
+PQB_DEFINE_PLUGIN(aroon, F_AROON)
 
 // ---- candle symbols: the 61 cdl* functions (pattern.rs) in the reference's order, price.rs, bop ---------
 #define PQB_DEFINE_CDL(name, id)                                                                               \

@@ -181,6 +181,21 @@ def MINUS_DM(high, low, timeperiod: int = 14):
     return _call("minus_dm", [high, low], [timeperiod])
 
 
+def TRIX(real, timeperiod: int = 30):
+    """TRIX - 1-day Rate-Of-Change (ROC) of a Triple Smooth EMA (momentum.rs:544)"""
+    return _call("trix", [real], [timeperiod])
+
+
+def ULTOSC(high, low, close, timeperiod1: int = 7, timeperiod2: int = 14, timeperiod3: int = 28):
+    """ULTOSC - Ultimate Oscillator (momentum.rs:573)"""
+    return _call("ultosc", [high, low, close], [timeperiod1, timeperiod2, timeperiod3])
+
+
+def AROON(high, low, timeperiod: int = 14):
+    """AROON - Aroon (aroon_up, aroon_down) (momentum.rs:63, momentum.py:32-38)"""
+    return _call("aroon", [high, low], [timeperiod], ("aroon_up", "aroon_down"))
+
+
 def STOCH(high, low, close, fastk_period: int = 5, slowk_period: int = 3, slowk_matype: int = 0,
           slowd_period: int = 3, slowd_matype: int = 0):
     """STOCH - Stochastic (SlowK, SlowD).  The reference composes it in Python from polars rolling
@@ -230,4 +245,5 @@ def ADOSC(high, low, close, volume, fastperiod: int = 3, slowperiod: int = 10):
 
 __all__ = ["SMA", "EMA", "TEMA", "TRIMA", "MA", "BBANDS", "MIDPOINT", "MIDPRICE", "RSI", "MACD", "MACDFIX", "WILLR",
            "MOM", "ROC", "ROCP", "ROCR", "ROCR100", "CMO", "MFI", "CCI", "STOCH", "KDJ", "TRANGE", "ATR", "NATR",
-           "OBV", "AD", "ADOSC", "ADX", "ADXR", "DX", "PLUS_DI", "MINUS_DI", "PLUS_DM", "MINUS_DM"]
+           "OBV", "AD", "ADOSC", "ADX", "ADXR", "DX", "PLUS_DI", "MINUS_DI", "PLUS_DM", "MINUS_DM", "TRIX", "ULTOSC",
+           "AROON"]

@@ -14,15 +14,19 @@ pytestmark = pytest.mark.gpu
 import tolerances as T
 
 EXTRA_OUT = ("midpoint", "adosc", "mom", "roc", "rocp", "rocr", "rocr100", "cmo", "mfi", "cci",
-             "plus_dm", "minus_dm", "dx", "minus_di", "adx", "adxr")
+             "plus_dm", "minus_dm", "dx", "minus_di", "adx", "adxr", "trix", "ultosc", "aroon_up", "aroon_down")
 DM_OUT = ("plus_dm", "minus_dm", "dx", "minus_di", "adx", "adxr")
 
 
 def _refs(d, s, P):
     c, h, l, v = (d[f][s] for f in ("close", "high", "low", "volume"))
     dm = pqo.dm(h, l, c, P.get("dm_period", 14))             # calc_dm family, momentum.rs:668-727
+    au, ad_ = pqo.aroon(h, l, P.get("aroon_period", 14))
     return {
         **dm,
+        "trix": pqo.trix(c, P.get("trix_period", 30)),
+        "ultosc": pqo.ultosc(h, l, c, P.get("ultosc_period1", 7), P.get("ultosc_period2", 14), P.get("ultosc_period3", 28)),
+        "aroon_up": au, "aroon_down": ad_,
         "midpoint": pqo.midpoint(c, P["midpoint_period"]),
         "adosc": pqo.adosc(h, l, c, v, P["adosc_fast"], P["adosc_slow"]),
         "mom": pqo.mom(c, P["mom_period"]),
@@ -46,14 +50,17 @@ def _data():
 
 
 @pytest.mark.parametrize("periods", [dict(), dict(midpoint_period=5, adosc_fast=2, adosc_slow=7, mom_period=1, roc_period=3,
-                                                  cmo_period=1, mfi_period=2, cci_period=1, dm_period=1),
+                                                  cmo_period=1, mfi_period=2, cci_period=1, dm_period=1,
+                                                  trix_period=1, ultosc_period1=1, ultosc_period2=2, ultosc_period3=3, aroon_period=1),
                                      dict(midpoint_period=60, adosc_fast=30, adosc_slow=12, mom_period=55, roc_period=41,
-                                          cmo_period=33, mfi_period=29, cci_period=47, dm_period=37)])
+                                          cmo_period=33, mfi_period=29, cci_period=47, dm_period=37,
+                                          trix_period=21, ultosc_period1=12, ultosc_period2=9, ultosc_period3=20, aroon_period=21)])
 def test_optional_groups_alone_and_with_the_suite(periods):
     import polars_quant_b200 as pq
     from polars_quant_b200 import _native as N
     P = dict(midpoint_period=14, adosc_fast=3, adosc_slow=10, mom_period=10, roc_period=10, cmo_period=14,
-             mfi_period=14, cci_period=14, dm_period=14)
+             mfi_period=14, cci_period=14, dm_period=14, trix_period=30, ultosc_period1=7, ultosc_period2=14,
+             ultosc_period3=28, aroon_period=14)
     P.update(periods)
     d = _data()
     S, NB = d["close"].shape
@@ -73,7 +80,8 @@ def test_optional_groups_alone_and_with_the_suite(periods):
     # one group at a time
     for g, bit in N.IND_EXTRA.items():
         res = panel.compute(N.default_params(indicators=bit, **P))
-        names = ("roc", "rocp", "rocr", "rocr100") if g == "roc" else DM_OUT if g == "dm" else (g,)
+        names = (("roc", "rocp", "rocr", "rocr100") if g == "roc" else DM_OUT if g == "dm"
+                 else ("aroon_up", "aroon_down") if g == "aroon" else (g,))
         for s in (0, 5, 6, 7, 8, 36):
             refs = _refs(d, s, P)
             for name in names:
@@ -89,7 +97,8 @@ def test_optional_groups_with_leading_nulls_and_host_pipeline():
     S, NB = d["close"].shape
     starts = np.random.default_rng(4).integers(0, 120, S).astype(np.int32)
     P = dict(midpoint_period=14, adosc_fast=3, adosc_slow=10, mom_period=10, roc_period=10, cmo_period=14,
-             mfi_period=14, cci_period=14, dm_period=14)
+             mfi_period=14, cci_period=14, dm_period=14, trix_period=30, ultosc_period1=7, ultosc_period2=14,
+             ultosc_period3=28, aroon_period=14)
     panel = pq.Panel(S, NB, outputs_mask=(1 << N.N_OUTPUTS) - 1)
     panel.set_fields(d["close"], d["high"], d["low"], d["volume"], starts=starts)
     panel.run_host(N.default_params(indicators=sum(N.IND_EXTRA.values()) | N.IND_ALL), chunk_symbols=32)
@@ -166,3 +175,35 @@ def test_directional_movement_family_quirks_and_plugin_names():
     assert talib.ADX(ah, al, ac, 0).null_count == 400         # calc_rma guard (D1)
     with pytest.raises(plugin.PluginError, match="not contiguous"):
         talib.ADX(pa.array(h, mask=np.arange(400) == 100), al, ac)
+
+
+def test_trix_ultosc_aroon_through_the_plugin_names_and_edge_cases():
+    import pyarrow as pa
+    from polars_quant_b200 import plugin, talib
+    d = synth.ohlcv(1, 300, seed=91)
+    h, l, c = d["high"][0].copy(), d["low"][0].copy(), d["close"][0].copy()
+    h[100:140] = l[100:140] = c[100:140] = c[99]              # a halt: ultosc range sums hit 0, aroon ties resolve to the LAST bar
+    ah, al, ac = pa.array(h), pa.array(l), pa.array(c)
+
+    def same(name, got, r):
+        ok = ~np.asarray(got.is_null())
+        v = np.where(ok, np.asarray(got.to_numpy(zero_copy_only=False), dtype=np.float64), np.nan)
+        nbad, msg = T.compare(name, v, ok, r[0], r[1])
+        assert nbad == 0, msg
+
+    same("trix", talib.TRIX(ac), pqo.trix(c, 30))
+    same("trix(5)", talib.TRIX(ac, 5), pqo.trix(c, 5))
+    ref = pqo.ultosc(h, l, c)
+    assert not ref[1][110:135].all()                          # the 7-bar range sum is 0 inside the halt -> nulls
+    same("ultosc", talib.ULTOSC(ah, al, ac), ref)
+    same("ultosc(3,5,9)", talib.ULTOSC(ah, al, ac, 3, 5, 9), pqo.ultosc(h, l, c, 3, 5, 9))
+    up, dn = talib.AROON(ah, al)
+    ru, rd = pqo.aroon(h, l, 14)
+    same("aroon_up", up, ru); same("aroon_down", dn, rd)
+    assert ru[0][130] == 100.0 and rd[0][130] == 100.0        # all-equal window: `>=` / `<=` keep the last index
+    assert plugin.output_field("aroon", [pa.field("h", pa.float64())]).name == "aroon"
+    with pytest.raises(plugin.PluginError, match="not contiguous"):
+        talib.TRIX(pa.array(c, mask=np.arange(300) == 7))
+    assert talib.TRIX(ac, 0).null_count == 300
+    with pytest.raises(plugin.PluginError, match="not built"):
+        talib.AROON(ah, al, 0)

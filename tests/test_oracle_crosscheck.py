@@ -41,6 +41,10 @@ def test_random_columns(seed):
         for k in ("plus_dm", "minus_dm", "dx", "minus_di", "adx", "adxr"):
             _eq(dm_c[k], dm_p[k], "dm." + k)
         _eq(dm_c["dx"], dm_p["plus_di"], "plus_di == dx (momentum.rs:409)")
+        _eq(pqo.trix(c, p), R.trix(co, p), "trix")
+        _eq(pqo.ultosc(h, l, c, p, p + 3, 2 * p + 1), R.ultosc(ho, lo, co, p, p + 3, 2 * p + 1), "ultosc")
+        for a, b in zip(pqo.aroon(h, l, p), R.aroon(ho, lo, p)):
+            _eq(a, b, "aroon")
     _eq(pqo.obv(c, v, okp, okp), R.obv(co, vo), "obv")
     _eq(pqo.ad(h, l, c, v, okp, okp, okp, okp), R.calc_ad(ho, lo, co, vo), "ad")
     _eq(pqo.adosc(h, l, c, v, 3, 10, okp, okp, okp, okp), R.adosc(ho, lo, co, vo, 3, 10), "adosc")
