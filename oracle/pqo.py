@@ -25,13 +25,15 @@ class OracleError(Exception):
         self.code = code
 
 
+_SO_CANDLES = _HERE / "libpq_candles.so"
+
+
 def build(force: bool = False) -> Path:
-    src = _HERE / "pq_oracle.c"
-    if force or not _SO.exists() or _SO.stat().st_mtime < src.stat().st_mtime:
-        env = dict(os.environ)
-        env.setdefault("CC", "gcc")
-        subprocess.run(["make", "-C", str(_HERE), "-B", "libpq_oracle.so"], check=True, env=env,
-                       stdout=subprocess.DEVNULL)
+    for so, src in ((_SO, _HERE / "pq_oracle.c"), (_SO_CANDLES, _HERE / "pq_candles.c")):
+        if force or not so.exists() or so.stat().st_mtime < src.stat().st_mtime:
+            env = dict(os.environ)
+            env.setdefault("CC", "gcc")
+            subprocess.run(["make", "-C", str(_HERE), "-B", so.name], check=True, env=env, stdout=subprocess.DEVNULL)
     return _SO
 
 
@@ -241,3 +243,48 @@ def suite_panel(c, h, l, v, params: SuiteParams | None = None, threads: int = 0)
     if rc < 0:
         raise OracleError(rc)
     return out, ok.astype(bool), rc
+
+
+# ---- candles (oracle/pq_candles.c): patterns, price transforms, bop ---------------------------------------------
+_clib = None
+
+
+def candles_lib():
+    global _clib
+    if _clib is None:
+        build()
+        _clib = C.CDLL(str(_SO_CANDLES))
+    return _clib
+
+
+def cdl(pattern: int, o, h, l, c, penetration: float = 0.3):
+    """One candlestick pattern (id in the reference's order of definition) on one symbol -> int32 array."""
+    o, h, l, c = (np.ascontiguousarray(x, dtype=np.float64) for x in (o, h, l, c))
+    out = np.empty(len(o), dtype=np.int32)
+    rc = candles_lib().pqc_pattern(C.c_int(pattern), _p(o), _p(h), _p(l), _p(c), C.c_int64(len(o)), C.c_double(penetration), _p(out))
+    if rc != 0:
+        raise OracleError(rc)
+    return out
+
+
+def price(which: int, o, h, l, c):
+    """avgprice 0, medprice 1, typprice 2, wclprice 3, bop 4 on null-free columns."""
+    o, h, l, c = (np.ascontiguousarray(x, dtype=np.float64) for x in (o, h, l, c))
+    out = np.empty(len(o), dtype=np.float64)
+    rc = candles_lib().pqc_price(C.c_int(which), _p(o), _p(h), _p(l), _p(c), C.c_int64(len(o)), _p(out))
+    if rc != 0:
+        raise OracleError(rc)
+    return out
+
+
+def candles_panel(o, h, l, c, penetration: float = 0.3, threads: int = 0):
+    """All 61 patterns + 5 price outputs over [n_symbols, n_bars] arrays -> (int32 [61, S, N], float64 [5, S, N], threads)."""
+    o, h, l, c = (np.ascontiguousarray(x, dtype=np.float64) for x in (o, h, l, c))
+    S, N = o.shape
+    pat = np.empty((61, S, N), dtype=np.int32)
+    pr = np.empty((5, S, N), dtype=np.float64)
+    used = candles_lib().pqc_panel(_p(o), _p(h), _p(l), _p(c), C.c_int64(S), C.c_int64(N), C.c_int64(N), C.c_double(penetration),
+                                   _p(pat), _p(pr), C.c_int(threads))
+    if used <= 0:
+        raise OracleError(used)
+    return pat, pr, used

@@ -43,6 +43,21 @@ for spec in specs:
         fired = int(sum((p.pattern(k) != 0).sum() for k in range(61)))
         rec.update({"e2e_ms": dt * 1e3, "e2e_symbol_bars_per_s": S * N / dt, "h2d_bytes": 32 * S * N,
                     "d2h_bytes": (61 * 4 + 5 * 8) * S * N, "pattern_hits": fired})
+    if host and "--no-cpu" not in sys.argv:
+        # CPU baseline beside it: oracle/pq_candles.c (the reference's per-function loops, 66 passes per symbol) on a
+        # bounded sample of the same panel, all host cores
+        import os, time
+        sys.path.insert(0, str(ROOT))
+        from oracle import pqo
+        ns = min(S, 16 * (os.cpu_count() or 1))
+        cols = [np.ascontiguousarray(p.host_field(f)[:ns]) for f in range(4)]
+        pqo.candles_panel(*cols)
+        t0 = time.perf_counter(); reps = 0
+        while time.perf_counter() - t0 < 10.0:
+            _, _, used = pqo.candles_panel(*cols); reps += 1
+        dt = time.perf_counter() - t0
+        rec["cpu_baseline"] = {"value": ns * N * reps / dt, "unit": "symbol*bars/s", "cores": used, "kind": "port",
+                               "sample": f"{ns} symbols x {N} bars of the same panel, {reps} passes, oracle/pq_candles.c"}
     print(json.dumps(rec))
     out.append(rec)
     p.close()

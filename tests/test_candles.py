@@ -70,3 +70,22 @@ def test_candle_entry_points_fail_loudly_without_a_device():
     out = np.zeros(8, dtype=np.int32)
     rc = N.lib().pqb_cdl(None, 3, C.byref(col), C.byref(col), C.byref(col), C.byref(col), 0.3, out.ctypes.data_as(C.c_void_p))
     assert rc == -3
+
+
+def test_c_oracle_reproduces_every_golden_column(g):
+    """oracle/pq_candles.c (the reference's per-function loops restated in C) against the vectors made by executing the
+    reference's own text: all 61 patterns, both penetration settings, the price transforms and BOP, exactly."""
+    from oracle import pqo
+    o, h, l, c = (g[k] for k in ("open", "high", "low", "close"))
+    pat, pr, used = pqo.candles_panel(o, h, l, c)
+    names = [str(n) for n in g["names"]]
+    assert used >= 1
+    for k, n in enumerate(names):
+        assert np.array_equal(pat[k], g["patterns"][k].astype(np.int32)), n
+    for k in range(5):
+        assert np.array_equal(pr[k].view(np.uint64), g["prices"][k].view(np.uint64)), k
+    pv = float(g["penetration_value"])
+    for j, n in enumerate(str(x) for x in g["penetration_names"]):
+        k = names.index(n)
+        for s in range(0, o.shape[0], 7):
+            assert np.array_equal(pqo.cdl(k, o[s], h[s], l[s], c[s], pv), g["patterns_pen"][j][s]), n

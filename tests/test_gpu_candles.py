@@ -164,3 +164,29 @@ def test_candle_functions_through_the_polars_plugin_symbols(g):
         plugin.call("cdldoji", [o, hn, l, c])                           # pattern.rs:14 cont_slice()?
     with pytest.raises(plugin.PluginError, match="not contiguous"):
         plugin.call("bop", [o, hn, l, c])                               # momentum.rs:119
+
+
+def test_config2_size_panels_against_the_c_oracle():
+    """Beyond the golden panel: full BASELINE config-2 shape (5,000 x 2,520) of random-walk OHLC and of the busy
+    synthetic candles, every pattern column and price output against oracle/pq_candles.c, bit for bit."""
+    from oracle import pqo
+    S, n = 5000, 2520
+    p = candles.CandlePanel(S, n)
+    for fill in ("walk", "busy"):
+        if fill == "walk":
+            p.fill_random_walk(seed=0xC0FFEE, sigma=0.02, to_host=True)
+        else:
+            p.fill_synthetic(seed=17, to_host=True)
+        p.run_host()
+        o, h, l, c = (np.ascontiguousarray(p.host_field(f)) for f in range(4))
+        pat, pr, _ = pqo.candles_panel(o, h, l, c)
+        hits = 0
+        for k in range(N.N_PATTERNS):
+            got = p.pattern(k)
+            assert np.array_equal(got, pat[k]), (fill, candles.pattern_names()[k], int((got != pat[k]).sum()))
+            hits += int((got != 0).sum())
+        assert hits > 1_000_000
+        for k in range(N.N_PRICES):
+            v, ok = p.price(k)
+            assert ok.all() and np.array_equal(v.view(np.uint64), pr[k].view(np.uint64)), (fill, N.PRICE_NAMES[k])
+    p.close()
