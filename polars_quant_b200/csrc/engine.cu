@@ -166,6 +166,8 @@ extern "C" int pqb_engine_create(int device, pqb_engine **out) {
     CU(cudaFuncSetAttribute(suite_fused_kernel<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     CU(cudaFuncSetAttribute(suite_fused_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
     CU(cudaFuncSetAttribute(suite_fused_kernel<false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    CU(cudaFuncSetAttribute(suite_fused_kernel<true, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+    CU(cudaFuncSetAttribute(suite_fused_kernel<true, false, false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     CU(cudaFuncSetAttribute(suite_fused_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
     CU(cudaFuncSetAttribute(suite_fused_kernel<false, false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     CU(cudaFuncSetAttribute(suite_fused_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
@@ -855,11 +857,19 @@ static int launch_suite(pqb_panel *p, const Built &full, int64_t b0, int64_t nb,
         unsigned grid = (unsigned)nb;
         const char *ts = getenv("PQB_TAIL_SPLIT");
         const bool tail_ok = !ts || atoi(ts) != 0;
+        const char *ps = getenv("PQB_PIPELINE");
+        const bool pipe_ok = !ps || atoi(ps) != 0;
         if (tail_ok && nb > e->sm_count && nb <= e->sm_count + e->sm_count / N_ROLES) {
             a.split_from = e->sm_count;
             grid = (unsigned)(e->sm_count + (nb - e->sm_count) * N_ROLES);
         }
         if (a.vmask) suite_fused_kernel<false, true><<<grid, CTA_THREADS, a.smem_bytes, e->stream>>>(a);
+        // small panels (about one CTA per SM) are bound by the length of each role's dependent FP64 chain per bar, not by
+        // issue slots or HBM: they run the variant whose division-heavy roles (BBANDS, RSI, STOCH) are software-pipelined
+        // over bars (suite_kernel.cuh "software-pipelined steady bar"); large panels are throughput-bound and run the
+        // plain one (the pipelined loops execute more instructions)
+        else if (fulls && pipe_ok && nb <= e->sm_count + e->sm_count / N_ROLES)
+            suite_fused_kernel<true, false, false, true><<<grid, CTA_THREADS, a.smem_bytes, e->stream>>>(a);
         else if (fulls) suite_fused_kernel<true, false><<<grid, CTA_THREADS, a.smem_bytes, e->stream>>>(a);
         else if (!(a.gmask & ~(unsigned)G_ALL)) suite_fused_kernel<false, false, true><<<grid, CTA_THREADS, a.smem_bytes, e->stream>>>(a);
         else suite_fused_kernel<false, false><<<grid, CTA_THREADS, a.smem_bytes, e->stream>>>(a);
@@ -1193,6 +1203,30 @@ extern "C" int pqb_flush_l2(pqb_engine *e) {
     }
     flush_kernel<<<e->sm_count * 4, 256, 0, e->stream>>>((uint4 *)e->flush_buf, e->flush_bytes / 16);
     CU(cudaGetLastError());
+    return PQB_OK;
+}
+
+extern "C" int pqb_selftest_divsqrt(pqb_engine *e, const double *a, const double *b, int64_t n, uint64_t result[4]) {
+    if (!e || !a || !b || !result || n <= 0) return fail(PQB_ERR_INVALID, "pqb_selftest_divsqrt: bad arguments");
+    int rc = set_dev(e);
+    if (rc) return rc;
+    double *da = nullptr, *db = nullptr;
+    unsigned long long *dr = nullptr;
+    CU(cudaMalloc(&da, n * sizeof(double)));
+    CU(cudaMalloc(&db, n * sizeof(double)));
+    CU(cudaMalloc(&dr, 4 * sizeof(unsigned long long)));
+    CU(cudaMemcpyAsync(da, a, n * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+    CU(cudaMemcpyAsync(db, b, n * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+    CU(cudaMemsetAsync(dr, 0, 4 * sizeof(unsigned long long), e->stream));
+    divsqrt_selftest_kernel<<<(unsigned)((n + 255) / 256), 256, 0, e->stream>>>(da, db, n, dr);
+    CU(cudaGetLastError());
+    unsigned long long hr[4];
+    CU(cudaMemcpyAsync(hr, dr, sizeof(hr), cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    for (int i = 0; i < 4; ++i) result[i] = hr[i];
+    cudaFree(da);
+    cudaFree(db);
+    cudaFree(dr);
     return PQB_OK;
 }
 
