@@ -225,7 +225,19 @@ def main():
         # NCCL prints its version banner (NCCL_DEBUG=VERSION/INFO in some images) on stdout: keep stdout
         # to the one JSON line of the contract
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # ... and some builds print it with a plain printf when the communicator is created: point fd 1 at stderr
+        # until the first collective has run
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
 
     import polars_quant_b200 as pq
     from polars_quant_b200 import _native as NV
