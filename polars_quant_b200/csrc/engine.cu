@@ -748,6 +748,12 @@ static int build_args(const pqb_panel *p, const pqb_suite_params *sp, Built *out
     if (A.gmask & (G_OBV | G_AD | G_ADOSC | G_MFI)) A.fields |= F_V;
 
     // shared-memory rings (slots of 32 doubles)
+    const bool mid_shares = (A.gmask & G_WILLR) && A.willr_p == A.mid_p;
+    // MIDPRICE shares WILLR's arrays when the windows are equal -- except for the full suite on a small panel, where the
+    // nine-warp variant runs it in a warp of its own (launch_suite picks that variant only if these arrays exist)
+    A.mid_own = (A.gmask & G_MIDPRICE) &&
+                (!mid_shares || (A.gmask == G_ALL && p->n_blocks <= p->e->sm_count + p->e->sm_count / N_ROLES_X));
+retry_layout:
     long long off = 0;
     auto take = [&](int slots) { const long long o = off; off += (long long)std::max(slots, 1) * SYM; return (int)std::min<long long>(o, 1ll << 30); };
     A.sring_slots = (A.gmask & G_SMA) ? A.sma_p : 1; A.off_sring = take(A.sring_slots);
@@ -758,7 +764,7 @@ static int build_args(const pqb_panel *p, const pqb_suite_params *sp, Built *out
     A.sk_slots = (A.gmask & G_KDJ) ? A.kdj_sd : 1; A.off_sk = take(A.sk_slots);
     // van Herk arrays: p slots + 1 sentinel each
     const int wp = (A.gmask & G_WILLR) ? A.willr_p + 1 : 0;
-    const int mp = ((A.gmask & G_MIDPRICE) && !((A.gmask & G_WILLR) && A.willr_p == A.mid_p)) ? A.mid_p + 1 : 0;
+    const int mp = A.mid_own ? A.mid_p + 1 : 0;
     const int kp = (A.gmask & G_KDJ) ? A.kdj_k + 1 : 0;
     A.off_wh = take(wp); A.off_wl = take(wp);
     A.off_mh = take(mp); A.off_ml = take(mp);
@@ -773,6 +779,7 @@ static int build_args(const pqb_panel *p, const pqb_suite_params *sp, Built *out
     A.off_ult = take((A.gmask & G_ULTOSC) ? 2 * std::max(std::max(A.ult_p1, A.ult_p2), A.ult_p3) : 2);
     A.off_arh = take((A.gmask & G_AROON) ? A.aroon_p + 1 : 0); A.off_arl = take((A.gmask & G_AROON) ? A.aroon_p + 1 : 0);
     const long long smem = (long long)kFixedSmem + off * 8;
+    if (smem > kMaxSmem && A.mid_own && mid_shares) { A.mid_own = 0; goto retry_layout; }   // long windows: share after all
     if (smem > kMaxSmem)
         return fail(PQB_ERR_UNSUPPORTED,
                     "windows too long for one launch: the per-block rings need %lld bytes of shared memory (limit %d); "
@@ -859,17 +866,20 @@ static int launch_suite(pqb_panel *p, const Built &full, int64_t b0, int64_t nb,
         const bool tail_ok = !ts || atoi(ts) != 0;
         const char *ps = getenv("PQB_PIPELINE");
         const bool pipe_ok = !ps || atoi(ps) != 0;
-        if (tail_ok && nb > e->sm_count && nb <= e->sm_count + e->sm_count / N_ROLES) {
+        // the small-panel variant: nine role warps (two CTAs of 320 threads fit an SM)
+        const bool small = fulls && pipe_ok && !a.vmask && a.mid_own && nb <= e->sm_count + e->sm_count / N_ROLES_X;
+        const int nr = small ? N_ROLES_X : N_ROLES;
+        if (tail_ok && nb > e->sm_count && nb <= e->sm_count + e->sm_count / nr) {
             a.split_from = e->sm_count;
-            grid = (unsigned)(e->sm_count + (nb - e->sm_count) * N_ROLES);
+            grid = (unsigned)(e->sm_count + (nb - e->sm_count) * nr);
         }
         if (a.vmask) suite_fused_kernel<false, true><<<grid, CTA_THREADS, a.smem_bytes, e->stream>>>(a);
         // small panels (about one CTA per SM) are bound by the length of each role's dependent FP64 chain per bar, not by
         // issue slots or HBM: they run the variant whose division-heavy roles (BBANDS, RSI, STOCH) are software-pipelined
         // over bars (suite_kernel.cuh "software-pipelined steady bar"); large panels are throughput-bound and run the
         // plain one (the pipelined loops execute more instructions)
-        else if (fulls && pipe_ok && nb <= e->sm_count + e->sm_count / N_ROLES)
-            suite_fused_kernel<true, false, false, true><<<grid, CTA_THREADS, a.smem_bytes, e->stream>>>(a);
+        else if (small)
+            suite_fused_kernel<true, false, false, true><<<grid, CTA_THREADS_X, a.smem_bytes, e->stream>>>(a);
         else if (fulls) suite_fused_kernel<true, false><<<grid, CTA_THREADS, a.smem_bytes, e->stream>>>(a);
         else if (!(a.gmask & ~(unsigned)G_ALL)) suite_fused_kernel<false, false, true><<<grid, CTA_THREADS, a.smem_bytes, e->stream>>>(a);
         else suite_fused_kernel<false, false><<<grid, CTA_THREADS, a.smem_bytes, e->stream>>>(a);
