@@ -869,9 +869,12 @@ static int launch_suite(pqb_panel *p, const Built &full, int64_t b0, int64_t nb,
         // the small-panel variant: nine role warps (two CTAs of 320 threads fit an SM)
         const bool small = fulls && pipe_ok && !a.vmask && a.mid_own && nb <= e->sm_count + e->sm_count / N_ROLES_X;
         const int nr = small ? N_ROLES_X : N_ROLES;
+        int parts = nr;                                       // tail CTAs per split block (default: one role each)
+        if (const char *tp = getenv("PQB_TAIL_PARTS")) parts = std::max(1, std::min(nr, atoi(tp)));
+        a.split_parts = parts;
         if (tail_ok && nb > e->sm_count && nb <= e->sm_count + e->sm_count / nr) {
             a.split_from = e->sm_count;
-            grid = (unsigned)(e->sm_count + (nb - e->sm_count) * nr);
+            grid = (unsigned)(e->sm_count + (nb - e->sm_count) * parts);
         }
         if (a.vmask) suite_fused_kernel<false, true><<<grid, CTA_THREADS, a.smem_bytes, e->stream>>>(a);
         // small panels (about one CTA per SM) are bound by the length of each role's dependent FP64 chain per bar, not by
