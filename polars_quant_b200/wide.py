@@ -1,0 +1,208 @@
+"""Wide `{symbol}_{column}` panels: the data format on both sides of the hot path.
+
+The reference documents its panel format only in README.md:88-161: `load(folder, file_type, prefix, suffix,
+has_header)` reads one file per symbol (file name = symbol, a `date` column required), full-joins them on `date`
+and returns a DataFrame whose first column is `date` and whose other columns are `{symbol}_{column}`
+(`AAPL_open`, `AAPL_close`, ...).  Its indicator engine is then applied column by column through polars.
+Here the same wide table (pyarrow; polars is not in this image) goes to the GPU as ONE panel:
+
+    table = load("data/stocks", file_type=["parquet"])
+    wp = WidePanel(table)                       # {symbol}_{open,high,low,close,volume} -> device panel(s)
+    out = wp.suite()                            # date + {symbol}_{sma,ema,...,midprice}: 21 columns per symbol
+    cdl = wp.candles()                          # date + {symbol}_{cdl2crows,...,bop}
+
+Arrow validity goes in as is (a symbol listed later has leading nulls, a halt has interior nulls: the engine's
+null rules apply); results come back as Arrow arrays that alias the panel's pinned host
+buffers (zero copy; they keep the panel alive).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+import numpy as np
+import pyarrow as pa
+import pyarrow.compute as pc
+
+from . import _native as N
+from .candles import CandlePanel, default_params as candle_default_params, pattern_names
+from .panel import Engine, Panel
+
+SUITE_FIELDS = ("close", "high", "low", "volume")          # enum pqb_field order
+CANDLE_FIELDS = ("open", "high", "low", "close")           # enum pqb_candle_field order
+_READERS = ("parquet", "csv", "json", "feather", "ipc")    # (xlsx / xls of the README need a spreadsheet reader: not in this image)
+
+
+def _read(path: Path, kind: str, has_header: bool) -> pa.Table:
+    if kind == "parquet":
+        import pyarrow.parquet as pq
+        return pq.read_table(path)
+    if kind == "csv":
+        import pyarrow.csv as pcsv
+        ro = pcsv.ReadOptions(autogenerate_column_names=not has_header)
+        return pcsv.read_csv(path, read_options=ro)
+    if kind == "json":
+        import pyarrow.json as pjson
+        return pjson.read_json(path)
+    import pyarrow.feather as pf
+    return pf.read_table(path)
+
+
+def load(folder, file_type=None, prefix=None, suffix=None, has_header: bool = True) -> pa.Table:
+    """README.md:90-161 `load`: every file of `folder` with one of the `file_type` extensions (default: all supported)
+    whose stem starts with `prefix` / ends with `suffix` is one symbol (symbol = file stem); all are full-joined on
+    `date` (sorted ascending) into `date`, `{symbol}_{column}`..."""
+    folder = Path(folder)
+    kinds = [k.lower() for k in (file_type or _READERS)]
+    for k in kinds:
+        if k in ("xlsx", "xls"):
+            raise NotImplementedError("spreadsheet files need a reader that is not in this image")
+        if k not in _READERS:
+            raise ValueError("unsupported file type %r" % k)
+    files = sorted(p for p in folder.iterdir() if p.is_file() and p.suffix[1:].lower() in kinds
+                   and (prefix is None or p.stem.startswith(prefix)) and (suffix is None or p.stem.endswith(suffix)))
+    if not files:
+        raise FileNotFoundError("no matching files in %s" % folder)
+    per_symbol = {}
+    for p in files:
+        t = _read(p, p.suffix[1:].lower(), has_header)
+        if "date" not in t.column_names:
+            raise ValueError("%s has no `date` column" % p.name)
+        per_symbol[p.stem] = t
+    dates = pa.chunked_array([t["date"].combine_chunks().cast(next(iter(per_symbol.values()))["date"].type)
+                              for t in per_symbol.values()])
+    all_dates = pc.unique(dates.combine_chunks())
+    all_dates = all_dates.take(pc.sort_indices(all_dates))
+    cols, names = [all_dates], ["date"]
+    for sym, t in per_symbol.items():
+        idx = pc.index_in(all_dates, value_set=t["date"].combine_chunks().cast(all_dates.type))   # null where the symbol has no row
+        for name in t.column_names:
+            if name == "date":
+                continue
+            cols.append(t[name].combine_chunks().take(idx))
+            names.append("%s_%s" % (sym, name))
+    return pa.table(cols, names=names)
+
+
+def split_columns(table: pa.Table, fields):
+    """-> (symbols in order of first appearance, {field: {symbol: column name}}) for `{symbol}_{field}` columns."""
+    symbols, by_field = [], {f: {} for f in fields}
+    for name in table.column_names:
+        for f in fields:
+            if name.endswith("_" + f) and len(name) > len(f) + 1:
+                sym = name[: -len(f) - 1]
+                by_field[f][sym] = name
+                if sym not in symbols:
+                    symbols.append(sym)
+    return symbols, by_field
+
+
+def _f64(col) -> pa.Array:
+    a = col.combine_chunks() if isinstance(col, pa.ChunkedArray) else col
+    return a if a.type == pa.float64() else a.cast(pa.float64())
+
+
+def _set(setter, handle, symbol, field, arr: pa.Array, n):
+    bufs = arr.buffers()
+    vptr = C.c_void_p(bufs[0].address) if (bufs[0] is not None and arr.null_count) else None
+    N.check(setter(handle, symbol, field, C.c_void_p(bufs[1].address), vptr, arr.offset, n))
+
+
+class _Keep:
+    """Base object of the zero-copy result buffers: keeps the panel (its pinned memory) alive."""
+
+    def __init__(self, owner):
+        self.owner = owner
+
+
+class WidePanel:
+    """A wide `date` + `{symbol}_{column}` table on one B200."""
+
+    def __init__(self, table: pa.Table, engine: Engine | None = None):
+        self.table = table
+        self.engine = engine
+        self.dates = table["date"] if "date" in table.column_names else None
+        self.n_bars = table.num_rows
+        self._suite = None
+        self._candles = None
+
+    # ---- the 15-indicator suite (+ optional groups through `params.indicators`) ----
+    def suite(self, params: N.SuiteParams | None = None, outputs=None) -> pa.Table:
+        """Runs the fused suite over every symbol that has close / high / low / volume columns; returns `date` +
+        `{symbol}_{output}` for the requested output names (default: the 21 suite outputs)."""
+        symbols, cols = split_columns(self.table, SUITE_FIELDS)
+        symbols = [s for s in symbols if all(s in cols[f] for f in SUITE_FIELDS)]
+        if not symbols:
+            raise ValueError("no symbol has all of " + ", ".join("{symbol}_" + f for f in SUITE_FIELDS))
+        params = params or N.default_params()
+        names = list(outputs) if outputs is not None else N.OUTPUT_NAMES[:N.N_SUITE_OUTPUTS]
+        ks = [N.OUTPUT_NAMES.index(n) for n in names]
+        omask = sum(1 << k for k in ks)
+        p = Panel(len(symbols), self.n_bars, engine=self.engine, outputs_mask=omask)
+        keep = []
+        for s, sym in enumerate(symbols):
+            for f, fname in enumerate(SUITE_FIELDS):
+                arr = _f64(self.table[cols[fname][sym]])
+                keep.append(arr)
+                _set(N.lib().pqb_panel_set_column, p._h, s, f, arr, self.n_bars)
+        p.run_host(params)
+        self._suite = p
+        base = _Keep(p)
+        out_cols, out_names = ([self.dates], ["date"]) if self.dates is not None else ([], [])
+        vbytes = (self.n_bars + 7) // 8
+        for s, sym in enumerate(symbols):
+            for k, n in zip(ks, names):
+                vals = N.lib().pqb_panel_host_output(p._h, k) + s * p.pitch * 8
+                bits = N.lib().pqb_panel_host_validity(p._h, k) + s * p.validity_pitch
+                arr = pa.Array.from_buffers(pa.float64(), self.n_bars,
+                                            [pa.foreign_buffer(bits, vbytes, base), pa.foreign_buffer(vals, self.n_bars * 8, base)])
+                out_cols.append(arr)
+                out_names.append("%s_%s" % (sym, n))
+        return pa.table(out_cols, names=out_names)
+
+    # ---- candles: 61 cdl* patterns + price transforms + bop ----
+    def candles(self, params: N.CandleParams | None = None, patterns=None, prices=None, on_nulls: str = "error") -> pa.Table:
+        """`date` + `{symbol}_{cdl*}` (Int32) + `{symbol}_{avgprice,...,bop}`.  The reference's cdl* and bop fail on a
+        column with nulls (`cont_slice()?`): `on_nulls="error"` raises naming the symbols, `"skip"` leaves them out."""
+        symbols, cols = split_columns(self.table, CANDLE_FIELDS)
+        symbols = [s for s in symbols if all(s in cols[f] for f in CANDLE_FIELDS)]
+        if not symbols:
+            raise ValueError("no symbol has all of " + ", ".join("{symbol}_" + f for f in CANDLE_FIELDS))
+        with_nulls = [s for s in symbols if any(self.table[cols[f][s]].null_count for f in CANDLE_FIELDS)]
+        if with_nulls:
+            if on_nulls != "skip":
+                raise ValueError("open/high/low/close of %s have nulls: the reference's cdl* / bop refuse such columns "
+                                 "(cont_slice()?); pass on_nulls='skip' to leave them out" % ", ".join(with_nulls[:8]))
+            symbols = [s for s in symbols if s not in with_nulls]
+            if not symbols:
+                raise ValueError("every symbol has nulls in open/high/low/close")
+        all_names = pattern_names()
+        pat = list(patterns) if patterns is not None else all_names
+        prc = list(prices) if prices is not None else list(N.PRICE_NAMES)
+        pmask = sum(1 << all_names.index(n) for n in pat)
+        rmask = sum(1 << N.PRICE_NAMES.index(n) for n in prc)
+        cp = CandlePanel(len(symbols), self.n_bars, engine=self.engine, patterns_mask=pmask, prices_mask=rmask)
+        for s, sym in enumerate(symbols):
+            for f, fname in enumerate(CANDLE_FIELDS):
+                arr = _f64(self.table[cols[fname][sym]])
+                _set(N.lib().pqb_candles_set_column, cp._h, s, f, arr, self.n_bars)
+        prm = params or candle_default_params(pmask, rmask)
+        prm.patterns, prm.prices = pmask, rmask
+        cp.run_host(prm)
+        self._candles = cp
+        base = _Keep(cp)
+        out_cols, out_names = ([self.dates], ["date"]) if self.dates is not None else ([], [])
+        vbytes = (self.n_bars + 7) // 8
+        for s, sym in enumerate(symbols):
+            for n in pat:
+                ptr = N.lib().pqb_candles_host_pattern(cp._h, all_names.index(n)) + s * cp.pitch * 4
+                out_cols.append(pa.Array.from_buffers(pa.int32(), self.n_bars, [None, pa.foreign_buffer(ptr, self.n_bars * 4, base)]))
+                out_names.append("%s_%s" % (sym, n))
+            for n in prc:
+                k = N.PRICE_NAMES.index(n)
+                vals = N.lib().pqb_candles_host_price(cp._h, k) + s * cp.pitch * 8
+                bits = N.lib().pqb_candles_host_price_validity(cp._h, k) + s * cp.words_per_row * 4
+                out_cols.append(pa.Array.from_buffers(pa.float64(), self.n_bars,
+                                                      [pa.foreign_buffer(bits, vbytes, base), pa.foreign_buffer(vals, self.n_bars * 8, base)]))
+                out_names.append("%s_%s" % (sym, n))
+        return pa.table(out_cols, names=out_names)
