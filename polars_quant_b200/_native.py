@@ -132,6 +132,11 @@ def lib() -> C.CDLL:
         L.pqb_panel_tiled_shape.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
         L.pqb_suite_params_default.argtypes = [C.POINTER(SuiteParams)]
         L.pqb_suite_params_default.restype = None
+        L.pqb_signals_run.argtypes = [C.c_void_p, C.c_double, C.c_double]
+        L.pqb_panel_host_signal.argtypes = [C.c_void_p, C.c_int]
+        L.pqb_panel_host_signal.restype = C.c_void_p
+        L.pqb_panel_device_signal.argtypes = [C.c_void_p, C.c_int]
+        L.pqb_panel_device_signal.restype = C.c_void_p
         # time-split panels
         L.pqb_split_required_warmup.argtypes = [C.POINTER(SuiteParams)]
         L.pqb_split_required_warmup.restype = C.c_int64

@@ -132,6 +132,8 @@ struct pqb_panel {
     uint32_t *d_vmask = nullptr;                        // tiled [block][bar][4]
     uint32_t *d_ovm[PQB_N_OUTPUTS] = {};                // tiled [block][bar] per output
     uint8_t *d_flags = nullptr;
+    // crossover signals (signals_host.inc): row-major int8 planes, allocated on first use
+    int8_t *d_sig = nullptr, *h_sig = nullptr;
 };
 
 static int set_dev(const pqb_engine *e) {
@@ -280,6 +282,8 @@ extern "C" void pqb_panel_destroy(pqb_panel *p) {
     for (auto &q : p->d_ovm) if (q) cudaFree(q);
     if (p->d_vmask) cudaFree(p->d_vmask);
     if (p->d_flags) cudaFree(p->d_flags);
+    if (p->d_sig) cudaFree(p->d_sig);
+    if (p->h_sig) cudaFreeHost(p->h_sig);
     for (auto &q : p->h_in) if (q) cudaFreeHost(q);
     for (auto &q : p->h_out) if (q) cudaFreeHost(q);
     for (auto &q : p->h_bits) if (q) cudaFreeHost(q);
@@ -1598,3 +1602,4 @@ extern "C" int pqb_multi_run_host(pqb_multi *m, const pqb_suite_params *params) 
 
 #include "candles_host.inc"
 #include "split_host.inc"
+#include "signals_host.inc"

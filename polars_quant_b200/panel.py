@@ -156,6 +156,18 @@ class Panel:
                 res[name] = (self.host_output(k), self.host_validity(k))
         return res
 
+    SIGNALS = ("macd_cross", "kdj_cross", "rsi_cross")
+
+    def signals(self, oversold: float = 30.0, overbought: float = 70.0):
+        """Crossover signals (int8 +1 / -1 / 0) from the outputs of the last run: {name: [n_symbols, n_bars] array}."""
+        N.check(N.lib().pqb_signals_run(self._h, oversold, overbought))
+        res = {}
+        for q, name in enumerate(self.SIGNALS):
+            ptr = N.lib().pqb_panel_host_signal(self._h, q)
+            buf = (C.c_int8 * (self.n_symbols * self.pitch)).from_address(ptr)
+            res[name] = np.frombuffer(buf, dtype=np.int8).reshape(self.n_symbols, self.pitch)[:, :self.n_bars]
+        return res
+
     def last_launches(self) -> int:
         return N.lib().pqb_panel_last_launches(self._h)
 

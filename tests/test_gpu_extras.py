@@ -207,3 +207,47 @@ def test_trix_ultosc_aroon_through_the_plugin_names_and_edge_cases():
     assert talib.TRIX(ac, 0).null_count == 300
     with pytest.raises(plugin.PluginError, match="not built"):
         talib.AROON(ah, al, 0)
+
+
+def test_crossover_signals_are_exact_functions_of_the_suite_outputs():
+    """golden / death crosses of MACD and KDJ and the RSI zone exits as int8, computed on the device from
+    the suite's own outputs -- compared with the same rules evaluated in numpy on the oracle's outputs (the rules are
+    defined in include/pqb200.h; the reference has them only in its README)."""
+    import polars_quant_b200 as pq
+    d = synth.ohlcv(70, 900, seed=314)
+    starts = np.random.default_rng(2).integers(0, 60, 70).astype(np.int32)
+    panel = pq.Panel(70, 900)
+    panel.set_fields(d["close"], d["high"], d["low"], d["volume"], starts=starts)
+    panel.run_host()
+    sig = panel.signals(oversold=35.0, overbought=65.0)
+    res = panel.outputs()
+
+    def cross(a, b):
+        out = np.zeros(a.shape, dtype=np.int8)
+        with np.errstate(invalid="ignore"):
+            up = (a[:, 1:] > b[:, 1:]) & (a[:, :-1] <= b[:, :-1])
+            dn = (a[:, 1:] < b[:, 1:]) & (a[:, :-1] >= b[:, :-1])
+        out[:, 1:][up] = 1
+        out[:, 1:][dn] = -1
+        return out
+
+    val = lambda n: np.where(res[n][1], res[n][0], np.nan)          # nulls as NaN: every comparison false
+    assert np.array_equal(sig["macd_cross"], cross(val("macd"), val("macd_signal")))
+    assert np.array_equal(sig["kdj_cross"], cross(val("kdj_k"), val("kdj_d")))
+    r = val("rsi")
+    want = np.zeros(r.shape, dtype=np.int8)
+    with np.errstate(invalid="ignore"):
+        want[:, 1:][(r[:, 1:] > 35.0) & (r[:, :-1] <= 35.0)] = 1
+        want[:, 1:][(r[:, 1:] < 65.0) & (r[:, :-1] >= 65.0)] = -1
+    assert np.array_equal(sig["rsi_cross"], want)
+    for n in sig:
+        assert (sig[n] != 0).sum() > 500 and set(np.unique(sig[n]).tolist()) <= {-1, 0, 1}
+    # and against the oracle's own columns (the suite outputs are bit-exact, so the signals are too)
+    out, ok, _ = pqo.suite_panel(d["close"][:, :], d["high"], d["low"], d["volume"])
+    s = 5
+    a = int(starts[s])
+    m, ms = pqo.macd(d["close"][s][a:])[0:2]
+    mv = np.full(900, np.nan); sv = np.full(900, np.nan)
+    mv[a:] = np.where(m[1], m[0], np.nan); sv[a:] = np.where(ms[1], ms[0], np.nan)
+    assert np.array_equal(sig["macd_cross"][s], cross(mv[None, :], sv[None, :])[0])
+    panel.close()
