@@ -72,6 +72,14 @@ def test_suite_block_boundaries(pq, n_symbols):
     _run_vs_oracle(pq, d)
 
 
+@pytest.mark.parametrize("n_symbols", [4736, 5100, 5300, 5500])
+def test_suite_around_one_block_per_sm(pq, n_symbols):
+    """148 SMs: 148 blocks (nine-warp small-panel variant), 160 (same + tail CTAs of one role each), 166 (plain kernel +
+    7-role tail CTAs), 172 (plain, no tail spreading) -- every launch shape of launch_suite against the oracle, all symbols."""
+    d = synth.ohlcv(n_symbols, 200, seed=900 + n_symbols)
+    _run_vs_oracle(pq, d)
+
+
 def test_suite_leading_nulls(pq):
     """Symbols listed at different dates: per-symbol first valid bar (leading Arrow nulls)."""
     d = synth.ohlcv(40, 600, seed=7)
