@@ -623,6 +623,43 @@ EXPORT int pqo_aroon(const double *h, const uint8_t *hok, const double *l, const
     return PQO_OK;
 }
 
+/* ------------------------------------------------------------------ info (last-row reductions)
+ * README.md:832-851 `Selector.info()`: README-only in the reference (no source), so this is the DEFINITION the GPU
+ * kernel (csrc/info_host.inc) is checked against: T = n-1, `start` = first valid row, sums oldest -> newest.
+ * out[13]: price, high, low, volume, return_1d, return_5d, return_20d, volatility, ma_5, ma_10, ma_20,
+ * volume_ratio, amplitude; ok[k] = 0 (and NaN) where the statistic needs rows before `start`. */
+EXPORT int pqo_info(const double *c, const double *h, const double *l, const double *v, int64_t n, int64_t start,
+                    double *out, uint8_t *ok) {
+    if (n < 1 || start < 0) return PQO_ERR_SHAPE;
+    const int64_t T = n - 1, have = n - start;
+    static const int64_t lags[3] = {1, 5, 20}, mas[3] = {5, 10, 20};
+    for (int k = 0; k < 13; ++k) put_null(out, ok, k);
+    if (have < 1) return PQO_OK;
+    put_val(out, ok, 0, c[T]); put_val(out, ok, 1, h[T]); put_val(out, ok, 2, l[T]); put_val(out, ok, 3, v[T]);
+    for (int i = 0; i < 3; ++i)
+        if (have > lags[i]) put_val(out, ok, 4 + i, (c[T] / c[T - lags[i]] - 1.0) * 100.0);
+    if (have >= 21) {
+        double r[20], sum = 0.0, ss = 0.0;
+        for (int i = 0; i < 20; ++i) { r[i] = c[T - 19 + i] / c[T - 20 + i] - 1.0; sum += r[i]; }
+        const double m = sum / 20.0;
+        for (int i = 0; i < 20; ++i) { const double d = r[i] - m; ss += d * d; }
+        put_val(out, ok, 7, sqrt(ss / 19.0) * sqrt(252.0) * 100.0);
+    }
+    for (int i = 0; i < 3; ++i)
+        if (have >= mas[i]) {
+            double sum = 0.0;
+            for (int64_t t = T - mas[i] + 1; t <= T; ++t) sum += c[t];
+            put_val(out, ok, 8 + i, sum / (double)mas[i]);
+        }
+    if (have >= 5) {
+        double sum = 0.0;
+        for (int64_t t = T - 4; t <= T; ++t) sum += v[t];
+        put_val(out, ok, 11, v[T] / (sum / 5.0));
+    }
+    put_val(out, ok, 12, (h[T] - l[T]) / c[T] * 100.0);
+    return PQO_OK;
+}
+
 /* ------------------------------------------------------------------ willr
  * momentum.rs:630-662.  Brute-force window, f64::MIN/MAX init, Rust max/min. */
 EXPORT int pqo_willr(const double *h, const uint8_t *hok, const double *l, const uint8_t *lok,

@@ -288,3 +288,18 @@ def candles_panel(o, h, l, c, penetration: float = 0.3, threads: int = 0):
     if used <= 0:
         raise OracleError(used)
     return pat, pr, used
+
+
+INFO_NAMES = ["price", "high", "low", "volume", "return_1d", "return_5d", "return_20d", "volatility", "ma_5", "ma_10",
+              "ma_20", "volume_ratio", "amplitude"]
+
+
+def info(c, h, l, v, start: int = 0):
+    """Last-row reductions of one symbol (pqo_info) -> (float64[13], bool[13])."""
+    c, h, l, v = (np.ascontiguousarray(x, dtype=np.float64) for x in (c, h, l, v))
+    out = np.empty(13, dtype=np.float64)
+    ok = np.zeros(13, dtype=np.uint8)
+    rc = lib().pqo_info(_p(c), _p(h), _p(l), _p(v), C.c_int64(len(c)), C.c_int64(start), _p(out), _p(ok))
+    if rc != 0:
+        raise OracleError(rc)
+    return out, ok.astype(bool)

@@ -59,6 +59,8 @@ class CandleParams(C.Structure):
 N_PATTERNS = 61
 N_PRICES = 5
 PRICE_NAMES = ["avgprice", "medprice", "typprice", "wclprice", "bop"]
+INFO_NAMES = ["price", "high", "low", "volume", "return_1d", "return_5d", "return_20d", "volatility", "ma_5", "ma_10",
+              "ma_20", "volume_ratio", "amplitude"]      # enum pqb_info
 OPEN_, HIGH_, LOW_, CLOSE_ = 0, 1, 2, 3          # candle panel fields
 
 
@@ -137,6 +139,7 @@ def lib() -> C.CDLL:
         L.pqb_panel_host_signal.restype = C.c_void_p
         L.pqb_panel_device_signal.argtypes = [C.c_void_p, C.c_int]
         L.pqb_panel_device_signal.restype = C.c_void_p
+        L.pqb_panel_info.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         # time-split panels
         L.pqb_split_required_warmup.argtypes = [C.POINTER(SuiteParams)]
         L.pqb_split_required_warmup.restype = C.c_int64

@@ -134,6 +134,7 @@ struct pqb_panel {
     uint8_t *d_flags = nullptr;
     // crossover signals (signals_host.inc): row-major int8 planes, allocated on first use
     int8_t *d_sig = nullptr, *h_sig = nullptr;
+    bool inputs_resident = false;        // the tiled input planes hold the panel (upload / run_host / fill_synthetic)
 };
 
 static int set_dev(const pqb_engine *e) {
@@ -463,6 +464,7 @@ extern "C" int pqb_panel_upload(pqb_panel *p) {
         }
         if ((rc = launch_conv(p, true, rm, tl, n, s0, ns, st))) return rc;
     }
+    p->inputs_resident = true;
     return prepare_nulls(p, st);
 }
 
@@ -1078,6 +1080,7 @@ extern "C" int pqb_suite_run_host(pqb_panel *p, const pqb_suite_params *sp, int6
     for (auto &x : up) cudaEventDestroy(x);
     for (auto &x : done) cudaEventDestroy(x);
     p->last_launches = total_launches;
+    p->inputs_resident = true;
     return PQB_OK;
 }
 
@@ -1135,6 +1138,7 @@ extern "C" int pqb_panel_fill_synthetic(pqb_panel *p, uint64_t seed, double sigm
                                                                   p->d_in[PQB_VOLUME], (int)p->n_symbols, (int)p->n_bars,
                                                                   (int)p->bars_padded, seed, sigma);
     CU(cudaGetLastError());
+    p->inputs_resident = true;
     if (to_host && p->staging && (rc = download_planes(p, true))) return rc;
     CU(cudaStreamSynchronize(p->e->stream));
     return PQB_OK;
@@ -1603,3 +1607,4 @@ extern "C" int pqb_multi_run_host(pqb_multi *m, const pqb_suite_params *params) 
 #include "candles_host.inc"
 #include "split_host.inc"
 #include "signals_host.inc"
+#include "info_host.inc"

@@ -168,6 +168,15 @@ class Panel:
             res[name] = np.frombuffer(buf, dtype=np.int8).reshape(self.n_symbols, self.pitch)[:, :self.n_bars]
         return res
 
+    def info(self):
+        """Last-row reductions per symbol (the README's `Selector.info()` columns that come from close / high / low /
+        volume; include/pqb200.h `pqb_panel_info`): {name: (float64[n_symbols], bool[n_symbols] valid)}.  The inputs
+        must be on the device (upload / run_host / fill_synthetic)."""
+        out = np.empty((len(N.INFO_NAMES), self.n_symbols), dtype=np.float64)
+        ok = np.empty((len(N.INFO_NAMES), self.n_symbols), dtype=np.uint8)
+        N.check(N.lib().pqb_panel_info(self._h, out.ctypes.data, ok.ctypes.data))
+        return {name: (out[k], ok[k].astype(bool)) for k, name in enumerate(N.INFO_NAMES)}
+
     def last_launches(self) -> int:
         return N.lib().pqb_panel_last_launches(self._h)
 

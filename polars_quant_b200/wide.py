@@ -160,6 +160,34 @@ class WidePanel:
                 out_names.append("%s_%s" % (sym, n))
         return pa.table(out_cols, names=out_names)
 
+    # ---- Selector.info(): last-row reductions (README.md:832-851) ----
+    def info(self) -> pa.Table:
+        """One row per symbol with the README's 15 `Selector.info()` columns: symbol, price, open, high, low, volume,
+        return_1d / 5d / 20d, volatility, ma_5 / 10 / 20, volume_ratio, amplitude (arithmetic: include/pqb200.h
+        `pqb_panel_info`).  `open` is the last row of `{symbol}_open` (null when the table has no such column)."""
+        symbols, cols = split_columns(self.table, SUITE_FIELDS + ("open",))
+        symbols = [s for s in symbols if all(s in cols[f] for f in SUITE_FIELDS)]
+        if not symbols:
+            raise ValueError("no symbol has all of " + ", ".join("{symbol}_" + f for f in SUITE_FIELDS))
+        p = Panel(len(symbols), self.n_bars, engine=self.engine, outputs_mask=1)
+        keep = []
+        for s, sym in enumerate(symbols):
+            for f, fname in enumerate(SUITE_FIELDS):
+                arr = _f64(self.table[cols[fname][sym]])
+                keep.append(arr)
+                _set(N.lib().pqb_panel_set_column, p._h, s, f, arr, self.n_bars)
+        p.upload()
+        res = p.info()
+        last = self.n_bars - 1
+        opens = [self.table[cols["open"][s]][last].as_py() if s in cols["open"] else None for s in symbols]
+        out = {"symbol": pa.array(symbols), "price": None, "open": pa.array(opens, type=pa.float64())}
+        for name in N.INFO_NAMES:
+            v, ok = res[name]
+            out[name] = pa.array(v, mask=~ok)
+        order = ["symbol", "price", "open", "high", "low", "volume", "return_1d", "return_5d", "return_20d", "volatility",
+                 "ma_5", "ma_10", "ma_20", "volume_ratio", "amplitude"]
+        return pa.table([out[n] for n in order], names=order)
+
     # ---- candles: 61 cdl* patterns + price transforms + bop ----
     def candles(self, params: N.CandleParams | None = None, patterns=None, prices=None, on_nulls: str = "error") -> pa.Table:
         """`date` + `{symbol}_{cdl*}` (Int32) + `{symbol}_{avgprice,...,bop}`.  The reference's cdl* and bop fail on a

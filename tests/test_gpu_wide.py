@@ -9,6 +9,7 @@ import pytest
 import synth
 import tolerances as T
 from oracle import pqo
+import polars_quant_b200 as pqb
 from polars_quant_b200 import wide, _native as N
 from test_wide import _symbol_table
 
@@ -69,3 +70,43 @@ def test_wide_candles_and_null_refusal(tmp_path):
     assert np.array_equal(out["AAA_cdldoji"].to_numpy(), pqo.cdl(names.index("cdldoji"), o, h, l, c))
     assert np.array_equal(out["AAA_typprice"].to_numpy(), pqo.price(2, o, h, l, c))
     assert np.array_equal(out["AAA_bop"].to_numpy(), pqo.price(4, o, h, l, c))
+
+
+def test_info_last_row_reductions_match_the_oracle(tmp_path):
+    """Selector.info() columns (README-only in the reference; defined in include/pqb200.h): bit-exact against pqo_info,
+    with symbols listed 3 / 10 / 25 bars before the end (statistics that need more history are null)."""
+    S, NB = 70, 300
+    d = synth.ohlcv(S, NB, seed=21)
+    p = pqb.Panel(S, NB)
+    starts = np.zeros(S, dtype=np.int32)
+    starts[5], starts[33], starts[64], starts[69] = NB - 3, NB - 10, NB - 25, NB - 1
+    for s in range(S):
+        ok = np.arange(NB) >= starts[s]
+        for f, name in enumerate(("close", "high", "low", "volume")):
+            p.set_column(s, f, d[name][s], validity=None if starts[s] == 0 else np.packbits(ok, bitorder="little"))
+    p.upload()
+    got = p.info()
+    for s in range(S):
+        ref, rok = pqo.info(d["close"][s], d["high"][s], d["low"][s], d["volume"][s], int(starts[s]))
+        for k, name in enumerate(N.INFO_NAMES):
+            v, ok = got[name]
+            assert ok[s] == rok[k], (s, name)
+            if rok[k]:
+                assert v[s].view(np.uint64) == ref[k].view(np.uint64), (s, name, v[s], ref[k])
+            else:
+                assert np.isnan(v[s])
+    assert got["volatility"][1][64] and not got["volatility"][1][33] and got["ma_5"][1][33] and not got["ma_5"][1][5]
+    # the wide-table route: one row per symbol, the README's 15 columns in its order
+    pq.write_table(_symbol_table(1, list(range(0, 200))), tmp_path / "AAA.parquet")
+    pq.write_table(_symbol_table(2, list(range(190, 200))), tmp_path / "BBB.parquet")
+    t = wide.load(tmp_path)
+    info = wide.WidePanel(t).info()
+    assert info.column_names == ["symbol", "price", "open", "high", "low", "volume", "return_1d", "return_5d", "return_20d",
+                                 "volatility", "ma_5", "ma_10", "ma_20", "volume_ratio", "amplitude"]
+    assert info["symbol"].to_pylist() == ["AAA", "BBB"]
+    assert info["price"][0].as_py() == t["AAA_close"][199].as_py() and info["open"][1].as_py() == t["BBB_open"][199].as_py()
+    assert info["return_20d"][1].as_py() is None and info["return_5d"][1].as_py() is not None
+    c = np.asarray(t["AAA_close"].to_numpy(), dtype=np.float64)
+    assert info["ma_10"][0].as_py() == pytest.approx(c[-10:].mean(), rel=1e-14)
+    r = c[-20:] / c[-21:-1] - 1.0
+    assert info["volatility"][0].as_py() == pytest.approx(r.std(ddof=1) * np.sqrt(252.0) * 100.0, rel=1e-12)

@@ -96,3 +96,21 @@ def test_suite_panel_equals_single_calls():
     for j, (vals, okj) in enumerate(single):
         assert np.array_equal(ok[j, s], okj), pqo.OUTPUT_NAMES[j]
         assert np.array_equal(out[j, s][okj].view(np.uint64), vals[okj].view(np.uint64)), pqo.OUTPUT_NAMES[j]
+
+
+def test_info_oracle_against_numpy():
+    """pqo_info (the definition of the last-row reductions, README.md:832-851) against an independent numpy reading."""
+    import synth
+    d = synth.ohlcv(6, 120, seed=9)
+    for s in range(6):
+        c, h, l, v = (d[k][s] for k in ("close", "high", "low", "volume"))
+        out, ok = pqo.info(c, h, l, v)
+        assert ok.all()
+        r = c[-20:] / c[-21:-1] - 1.0
+        want = [c[-1], h[-1], l[-1], v[-1], (c[-1] / c[-2] - 1) * 100, (c[-1] / c[-6] - 1) * 100, (c[-1] / c[-21] - 1) * 100,
+                r.std(ddof=1) * np.sqrt(252.0) * 100, c[-5:].mean(), c[-10:].mean(), c[-20:].mean(), v[-1] / v[-5:].mean(),
+                (h[-1] - l[-1]) / c[-1] * 100]
+        assert np.allclose(out, want, rtol=1e-12, atol=0)
+        assert out[0] == want[0] and out[4] == want[4] and out[12] == want[12]          # single-operation columns: exact
+    out, ok = pqo.info(c, h, l, v, start=120 - 7)                                       # 7 valid rows at the end
+    assert ok.tolist() == [True] * 4 + [True, True, False, False, True, False, False, True, True]
