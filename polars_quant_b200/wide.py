@@ -84,6 +84,101 @@ def load(folder, file_type=None, prefix=None, suffix=None, has_header: bool = Tr
     return pa.table(cols, names=names)
 
 
+def prepare_sequential_data(folder_path, date_col: str = "date", symbol_col: str = "symbol", fill_null_strategy: str = "forward",
+                            default_fill_value: float = 0.0) -> pa.Table:
+    """python/polars_quant/backtest/sequential.py:7-93 over pyarrow: every .csv / .parquet / .pqt file of the folder (the
+    file stem is the symbol when the file has no `symbol_col`) is concatenated (union of the columns), aligned on the
+    full `unique dates x unique symbols` grid, sorted by (date, symbol), and its value columns are filled per symbol
+    ("forward", "backward" or "zero") and then with `default_fill_value` (what is still null, e.g. before a listing).
+    Returns the LONG table `date_col, symbol_col, value columns...`; `to_wide` pivots it into a `{symbol}_{column}` panel.
+    Value columns must be numeric (they come back as Float64); a (date, symbol) pair may appear only once."""
+    folder = Path(folder_path)
+    if not folder.exists() or not folder.is_dir():
+        raise FileNotFoundError("The directory '%s' does not exist or is not a directory." % folder_path)
+    frames = []
+    for p in sorted(folder.iterdir()):
+        ext = p.suffix.lower()
+        if ext == ".csv":
+            t = _read(p, "csv", True)
+        elif ext in (".parquet", ".pqt"):
+            t = _read(p, "parquet", True)
+        else:
+            continue
+        if symbol_col not in t.column_names:
+            t = t.append_column(symbol_col, pa.array([p.stem] * t.num_rows, type=pa.string()))
+        frames.append(t)
+    if not frames:
+        raise ValueError("No valid CSV or Parquet files found in '%s'." % folder_path)
+    value_cols = []
+    for t in frames:
+        value_cols += [c for c in t.column_names if c not in (date_col, symbol_col) and c not in value_cols]
+    date_type = frames[0][date_col].type
+    dates = pa.concat_arrays([t[date_col].combine_chunks().cast(date_type) for t in frames])
+    syms = pa.concat_arrays([t[symbol_col].combine_chunks().cast(pa.string()) for t in frames])
+    u_dates = pc.unique(dates)
+    u_dates = u_dates.take(pc.sort_indices(u_dates))
+    u_syms = pc.unique(syms)
+    u_syms = u_syms.take(pc.sort_indices(u_syms))
+    nd, ns = len(u_dates), len(u_syms)
+    di = np.asarray(pc.index_in(dates, value_set=u_dates).to_numpy(zero_copy_only=False), dtype=np.int64)
+    si = np.asarray(pc.index_in(syms, value_set=u_syms).to_numpy(zero_copy_only=False), dtype=np.int64)
+    cell = di * ns + si
+    if len(np.unique(cell)) != len(cell):
+        raise ValueError("a (%s, %s) pair appears more than once" % (date_col, symbol_col))
+    out_cols = [u_dates.take(pa.array(np.repeat(np.arange(nd), ns))), u_syms.take(pa.array(np.tile(np.arange(ns), nd)))]
+    row0 = np.cumsum([0] + [t.num_rows for t in frames])
+    for name in value_cols:
+        grid = np.full(nd * ns, np.nan)
+        have = np.zeros(nd * ns, dtype=bool)
+        for k, t in enumerate(frames):
+            if name not in t.column_names:
+                continue
+            a = _f64(t[name])
+            ok = ~np.asarray(a.is_null())
+            idx = cell[row0[k]:row0[k + 1]][ok]
+            grid[idx] = np.asarray(a.to_numpy(zero_copy_only=False), dtype=np.float64)[ok]
+            have[idx] = True
+        grid, have = grid.reshape(nd, ns), have.reshape(nd, ns)
+        if fill_null_strategy in ("forward", "backward"):
+            rows = np.arange(nd)[:, None]
+            if fill_null_strategy == "forward":
+                src = np.maximum.accumulate(np.where(have, rows, -1), axis=0)               # last valid row at or before
+                okf = src >= 0
+            else:
+                src = np.minimum.accumulate(np.where(have, rows, nd)[::-1], axis=0)[::-1]   # first valid row at or after
+                okf = src < nd
+            grid = np.where(okf, np.take_along_axis(grid, np.clip(src, 0, nd - 1), axis=0), np.nan)
+            have = okf
+        elif fill_null_strategy == "zero":
+            grid, have = np.where(have, grid, 0.0), np.ones_like(have)
+        grid = np.where(have, grid, float(default_fill_value))
+        out_cols.append(pa.array(grid.reshape(-1)))
+    return pa.table(out_cols, names=[date_col, symbol_col] + value_cols)
+
+
+def to_wide(long_table: pa.Table, date_col: str = "date", symbol_col: str = "symbol") -> pa.Table:
+    """Long (date, symbol, values...) -> the wide `date`, `{symbol}_{column}` panel of README.md:88-161 (what `load`
+    returns and `WidePanel` takes); (date, symbol) pairs that are absent become nulls."""
+    dates = long_table[date_col].combine_chunks()
+    syms = long_table[symbol_col].combine_chunks().cast(pa.string())
+    u_dates = pc.unique(dates)
+    u_dates = u_dates.take(pc.sort_indices(u_dates))
+    u_syms = pc.unique(syms)                                                              # order of first appearance
+    di = np.asarray(pc.index_in(dates, value_set=u_dates).to_numpy(zero_copy_only=False), dtype=np.int64)
+    si = np.asarray(pc.index_in(syms, value_set=u_syms).to_numpy(zero_copy_only=False), dtype=np.int64)
+    cols, names = [u_dates], ["date"]
+    value_cols = [c for c in long_table.column_names if c not in (date_col, symbol_col)]
+    for k, sym in enumerate(u_syms.to_pylist()):
+        rows = np.nonzero(si == k)[0]
+        where = np.full(len(u_dates), -1, dtype=np.int64)
+        where[di[rows]] = rows
+        take = pa.array(where, mask=where < 0)
+        for c in value_cols:
+            cols.append(long_table[c].combine_chunks().take(take))
+            names.append("%s_%s" % (sym, c))
+    return pa.table(cols, names=names)
+
+
 def split_columns(table: pa.Table, fields):
     """-> (symbols in order of first appearance, {field: {symbol: column name}}) for `{symbol}_{field}` columns."""
     symbols, by_field = [], {f: {} for f in fields}
