@@ -139,6 +139,7 @@ def lib() -> C.CDLL:
         L.pqb_panel_host_signal.restype = C.c_void_p
         L.pqb_panel_device_signal.argtypes = [C.c_void_p, C.c_int]
         L.pqb_panel_device_signal.restype = C.c_void_p
+        L.pqb_signals_time.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_int, C.c_int, C.POINTER(C.c_float)]
         L.pqb_panel_info.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         # time-split panels
         L.pqb_split_required_warmup.argtypes = [C.POINTER(SuiteParams)]

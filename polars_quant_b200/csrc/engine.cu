@@ -175,6 +175,10 @@ extern "C" int pqb_engine_create(int device, pqb_engine **out) {
     CU(cudaFuncSetAttribute(suite_fused_kernel<false, false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     CU(cudaFuncSetAttribute(suite_fused_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
     CU(cudaFuncSetAttribute(suite_fused_kernel<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    CU(cudaFuncSetAttribute(suite_fused_kernel<false, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+    CU(cudaFuncSetAttribute(suite_fused_kernel<false, false, false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    CU(cudaFuncSetAttribute(suite_fused_kernel<false, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+    CU(cudaFuncSetAttribute(suite_fused_kernel<false, true, false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     *out = e;
     return PQB_OK;
 }
@@ -874,7 +878,10 @@ static int launch_suite(pqb_panel *p, const Built &full, int64_t b0, int64_t nb,
         const bool pipe_ok = !ps || atoi(ps) != 0;
         // the small-panel variant: nine role warps (two CTAs of 320 threads fit an SM)
         const bool small = fulls && pipe_ok && !a.vmask && a.mid_own && nb <= e->sm_count + e->sm_count / N_ROLES_X;
-        const int nr = small ? N_ROLES_X : N_ROLES;
+        // optional groups: the eleven-slot general kernel (their long per-bar chains get warps of their own)
+        const char *ws = getenv("PQB_WIDE");
+        const bool wide = !fulls && (a.gmask & ~(unsigned)G_ALL) && (ws && atoi(ws) != 0);   // (opt-in until verified on the GPU)
+        const int nr = small ? N_ROLES_X : wide ? N_SLOTS_W : N_ROLES;
         int parts = nr;                                       // tail CTAs per split block (default: one role each)
         if (const char *tp = getenv("PQB_TAIL_PARTS")) parts = std::max(1, std::min(nr, atoi(tp)));
         a.split_parts = parts;
@@ -882,7 +889,8 @@ static int launch_suite(pqb_panel *p, const Built &full, int64_t b0, int64_t nb,
             a.split_from = e->sm_count;
             grid = (unsigned)(e->sm_count + (nb - e->sm_count) * parts);
         }
-        if (a.vmask) suite_fused_kernel<false, true><<<grid, CTA_THREADS, a.smem_bytes, e->stream>>>(a);
+        if (a.vmask && wide) suite_fused_kernel<false, true, false, true><<<grid, CTA_THREADS_W, a.smem_bytes, e->stream>>>(a);
+        else if (a.vmask) suite_fused_kernel<false, true><<<grid, CTA_THREADS, a.smem_bytes, e->stream>>>(a);
         // small panels (about one CTA per SM) are bound by the length of each role's dependent FP64 chain per bar, not by
         // issue slots or HBM: they run the variant whose division-heavy roles (BBANDS, RSI, STOCH) are software-pipelined
         // over bars (suite_kernel.cuh "software-pipelined steady bar"); large panels are throughput-bound and run the
@@ -891,6 +899,7 @@ static int launch_suite(pqb_panel *p, const Built &full, int64_t b0, int64_t nb,
             suite_fused_kernel<true, false, false, true><<<grid, CTA_THREADS_X, a.smem_bytes, e->stream>>>(a);
         else if (fulls) suite_fused_kernel<true, false><<<grid, CTA_THREADS, a.smem_bytes, e->stream>>>(a);
         else if (!(a.gmask & ~(unsigned)G_ALL)) suite_fused_kernel<false, false, true><<<grid, CTA_THREADS, a.smem_bytes, e->stream>>>(a);
+        else if (wide) suite_fused_kernel<false, false, false, true><<<grid, CTA_THREADS_W, a.smem_bytes, e->stream>>>(a);
         else suite_fused_kernel<false, false><<<grid, CTA_THREADS, a.smem_bytes, e->stream>>>(a);
         CU(cudaGetLastError());
         ++n_launch;
