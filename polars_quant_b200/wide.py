@@ -181,15 +181,13 @@ def to_wide(long_table: pa.Table, date_col: str = "date", symbol_col: str = "sym
 
 def split_columns(table: pa.Table, fields):
     """-> (symbols in order of first appearance, {field: {symbol: column name}}) for `{symbol}_{field}` columns."""
-    symbols, by_field = [], {f: {} for f in fields}
+    symbols, by_field = {}, {f: {} for f in fields}
     for name in table.column_names:
-        for f in fields:
-            if name.endswith("_" + f) and len(name) > len(f) + 1:
-                sym = name[: -len(f) - 1]
-                by_field[f][sym] = name
-                if sym not in symbols:
-                    symbols.append(sym)
-    return symbols, by_field
+        sym, sep, f = name.rpartition("_")
+        if sep and sym and f in by_field:
+            by_field[f][sym] = name
+            symbols.setdefault(sym, None)
+    return list(symbols), by_field
 
 
 def _f64(col) -> pa.Array:
@@ -218,8 +216,12 @@ class WidePanel:
         self.engine = engine
         self.dates = table["date"] if "date" in table.column_names else None
         self.n_bars = table.num_rows
+        self._index = {name: i for i, name in enumerate(table.column_names)}     # (Table[name] is slow on wide tables)
         self._suite = None
         self._candles = None
+
+    def _col(self, name):
+        return self.table.column(self._index[name])
 
     # ---- the 15-indicator suite (+ optional groups through `params.indicators`) ----
     def suite(self, params: N.SuiteParams | None = None, outputs=None) -> pa.Table:
@@ -233,11 +235,12 @@ class WidePanel:
         names = list(outputs) if outputs is not None else N.OUTPUT_NAMES[:N.N_SUITE_OUTPUTS]
         ks = [N.OUTPUT_NAMES.index(n) for n in names]
         omask = sum(1 << k for k in ks)
+        self._suite = None          # (an earlier panel no result refers to any more goes back to the engine's pinned pool first)
         p = Panel(len(symbols), self.n_bars, engine=self.engine, outputs_mask=omask)
         keep = []
         for s, sym in enumerate(symbols):
             for f, fname in enumerate(SUITE_FIELDS):
-                arr = _f64(self.table[cols[fname][sym]])
+                arr = _f64(self._col(cols[fname][sym]))
                 keep.append(arr)
                 _set(N.lib().pqb_panel_set_column, p._h, s, f, arr, self.n_bars)
         p.run_host(params)
@@ -268,13 +271,13 @@ class WidePanel:
         keep = []
         for s, sym in enumerate(symbols):
             for f, fname in enumerate(SUITE_FIELDS):
-                arr = _f64(self.table[cols[fname][sym]])
+                arr = _f64(self._col(cols[fname][sym]))
                 keep.append(arr)
                 _set(N.lib().pqb_panel_set_column, p._h, s, f, arr, self.n_bars)
         p.upload()
         res = p.info()
         last = self.n_bars - 1
-        opens = [self.table[cols["open"][s]][last].as_py() if s in cols["open"] else None for s in symbols]
+        opens = [self._col(cols["open"][s])[last].as_py() if s in cols["open"] else None for s in symbols]
         out = {"symbol": pa.array(symbols), "price": None, "open": pa.array(opens, type=pa.float64())}
         for name in N.INFO_NAMES:
             v, ok = res[name]
@@ -291,7 +294,7 @@ class WidePanel:
         symbols = [s for s in symbols if all(s in cols[f] for f in CANDLE_FIELDS)]
         if not symbols:
             raise ValueError("no symbol has all of " + ", ".join("{symbol}_" + f for f in CANDLE_FIELDS))
-        with_nulls = [s for s in symbols if any(self.table[cols[f][s]].null_count for f in CANDLE_FIELDS)]
+        with_nulls = [s for s in symbols if any(self._col(cols[f][s]).null_count for f in CANDLE_FIELDS)]
         if with_nulls:
             if on_nulls != "skip":
                 raise ValueError("open/high/low/close of %s have nulls: the reference's cdl* / bop refuse such columns "
@@ -307,7 +310,7 @@ class WidePanel:
         cp = CandlePanel(len(symbols), self.n_bars, engine=self.engine, patterns_mask=pmask, prices_mask=rmask)
         for s, sym in enumerate(symbols):
             for f, fname in enumerate(CANDLE_FIELDS):
-                arr = _f64(self.table[cols[fname][sym]])
+                arr = _f64(self._col(cols[fname][sym]))
                 _set(N.lib().pqb_candles_set_column, cp._h, s, f, arr, self.n_bars)
         prm = params or candle_default_params(pmask, rmask)
         prm.patterns, prm.prices = pmask, rmask

@@ -43,21 +43,26 @@ def kernel_rec(tag, S, NB, ms, bps, **extra):
 
 
 if "groups" in which:
-    S, NB = 10_000, 5_040
-    dm = ("plus_dm", "minus_dm", "dx", "minus_di", "adx", "adxr")
-    om = sum(1 << NAMES.index(o) for o in dm)
-    p = pq.Panel(S, NB, engine=eng, outputs_mask=om, host_staging=False)
-    p.fill_synthetic(seed=7)
-    tot, fused, nl = p.time_device(N.default_params(indicators=N.IND_EXTRA["dm"]), warmup=2, iters=5)
-    kernel_rec("dm family (plus_dm, minus_dm, dx, minus_di, adx, adxr)", S, NB, fused / 5, 72)
-    p.close()
-    om = (1 << N.N_OUTPUTS) - 1
-    p = pq.Panel(S, NB, engine=eng, outputs_mask=om, host_staging=False)
-    p.fill_synthetic(seed=7)
-    allg = N.IND_ALL | sum(N.IND_EXTRA.values())
-    tot, fused, nl = p.time_device(N.default_params(indicators=allg), warmup=2, iters=5)
-    kernel_rec("every group: 41 outputs", S, NB, fused / 5, 8 * (4 + N.N_OUTPUTS))
-    p.close()
+    # bytes per symbol-bar: 8 x (input planes the groups read + outputs they write); the suite + optional groups run as
+    # two launches that both read their inputs
+    OUTS = {"midpoint": 1, "adosc": 1, "mom": 1, "roc": 4, "cmo": 1, "mfi": 1, "cci": 1, "dm": 6, "trix": 1, "ultosc": 1, "aroon": 2}
+    INS = {"midpoint": 1, "adosc": 4, "mom": 1, "roc": 1, "cmo": 1, "mfi": 4, "cci": 3, "dm": 3, "trix": 1, "ultosc": 3, "aroon": 2}
+    for S in (10_000, 50_000):
+        NB = 5_040
+        p = pq.Panel(S, NB, engine=eng, outputs_mask=(1 << N.N_OUTPUTS) - 1, host_staging=False)
+        p.fill_synthetic(seed=7)
+        if S == 10_000:
+            for name, bit in N.IND_EXTRA.items():
+                tot, fused, nl = p.time_device(N.default_params(indicators=bit), warmup=1, iters=3)
+                kernel_rec("optional group alone: " + name, S, NB, fused / 3, 8 * (INS[name] + OUTS[name]))
+        tot, fused, nl = p.time_device(N.default_params(indicators=N.IND_ALL), warmup=1, iters=3)
+        kernel_rec("the 15-indicator suite (same panel)", S, NB, fused / 3, 200)
+        tot, fused, nl = p.time_device(N.default_params(indicators=N.IND_ALL | N.IND_EXTRA["mom"]), warmup=1, iters=3)
+        kernel_rec("suite + MOM (two launches)", S, NB, fused / 3, 200 + 16)
+        allg = N.IND_ALL | sum(N.IND_EXTRA.values())
+        tot, fused, nl = p.time_device(N.default_params(indicators=allg), warmup=1, iters=3)
+        kernel_rec("every group: 41 outputs (two launches)", S, NB, fused / 3, 8 * (4 + 21) + 8 * (4 + 20))
+        p.close()
 
 if "signals" in which:
     S, NB = 20_000, 5_040
