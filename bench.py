@@ -330,6 +330,16 @@ def main():
                                 "kernel": "candle_kernel<true>", "kernel_ms": msc, "value": Sc * Nc / (msc * 1e-3),
                                 "unit": "symbol*bars/s", "algorithmic_bytes_per_symbol_bar": 316, "achieved_gbs": gc,
                                 "frac": gc / peak}
+            # what HBM delivers for the suite's own access mix (4 planes read, 21 written, 256-byte warp rows) with no
+            # arithmetic at all: the copy bandwidth used as `peak` is a 1 : 1 mix, a write-heavy stream gets less
+            import ctypes as C
+            from polars_quant_b200 import _native as NN
+            msx = C.c_float()
+            NN.check(NN.lib().pqb_stream_mix(engine._h, N_IN, N_OUT, 20_000 * 5_040, 2, 5, C.byref(msx)))
+            gx = 8 * (N_IN + N_OUT) * 20_000 * 5_040 / (msx.value * 1e-3) / 1e9
+            other["access_mix_ceiling"] = {"workload": "streaming kernel, %d planes read : %d written, 20,000 x 5,040 doubles each, no arithmetic" % (N_IN, N_OUT),
+                                           "kernel": "stream_mix_kernel", "kernel_ms": msx.value, "achieved_gbs": gx, "frac": gx / peak,
+                                           "suite_over_mix": achieved / gx}
         except Exception as ex:          # never lose the headline line to an extra
             other["error"] = repr(ex)
 

@@ -1296,6 +1296,60 @@ __global__ void flush_kernel(uint4 *p, size_t n) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
         p[i] = make_uint4((unsigned)i, 1u, 2u, 3u);
 }
+// ---- measurement helper: what HBM delivers for a given read : write mix, without any indicator arithmetic ----
+// A grid-stride kernel reads `n_reads` planes and writes `n_writes` planes with the suite's own 256-byte warp rows
+// (streaming loads / stores).  bench.py runs it with the suite's mix (4 reads, 21 writes) next to the fused kernel:
+// the copy bandwidth in MEASURED_PEAKS.json is a 1 : 1 mix, and a write-heavy mix gets less out of HBM3e.
+struct MixArgs { const double *in[PQB_N_FIELDS]; double *out[PQB_N_OUTPUTS]; int n_in, n_out; };
+__global__ void __launch_bounds__(256) stream_mix_kernel(const __grid_constant__ MixArgs P, size_t n) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        double s = 0.0;
+        for (int f = 0; f < P.n_in; ++f) s += __ldcs(P.in[f] + i);
+        for (int k = 0; k < P.n_out; ++k) __stcs(P.out[k] + i, s + (double)k);
+    }
+}
+
+extern "C" int pqb_stream_mix(pqb_engine *e, int n_reads, int n_writes, int64_t doubles_per_plane, int warmup, int iters,
+                              float *ms_per_iter) {
+    if (!e || !ms_per_iter || n_reads < 0 || n_reads > PQB_N_FIELDS || n_writes < 1 || n_writes > PQB_N_OUTPUTS ||
+        doubles_per_plane < 1 || iters < 1)
+        return fail(PQB_ERR_INVALID, "pqb_stream_mix: bad argument");
+    int rc = set_dev(e);
+    if (rc) return rc;
+    MixArgs P{};
+    P.n_in = n_reads; P.n_out = n_writes;
+    const size_t bytes = (size_t)doubles_per_plane * sizeof(double);
+    std::vector<void *> owned;
+    auto release = [&]() { for (void *q : owned) cudaFree(q); };
+    cudaError_t ce = cudaSuccess;
+    for (int f = 0; f < n_reads && ce == cudaSuccess; ++f) {
+        void *q = nullptr;
+        if ((ce = cudaMalloc(&q, bytes)) == cudaSuccess) { owned.push_back(q); P.in[f] = (const double *)q; ce = cudaMemsetAsync(q, 0, bytes, e->stream); }
+    }
+    for (int k = 0; k < n_writes && ce == cudaSuccess; ++k) {
+        void *q = nullptr;
+        if ((ce = cudaMalloc(&q, bytes)) == cudaSuccess) { owned.push_back(q); P.out[k] = (double *)q; }
+    }
+    cudaEvent_t a = nullptr, b = nullptr;
+    if (ce == cudaSuccess) ce = cudaEventCreate(&a);
+    if (ce == cudaSuccess) ce = cudaEventCreate(&b);
+    const unsigned grid = (unsigned)e->sm_count * 8;
+    for (int i = 0; i < warmup && ce == cudaSuccess; ++i) { stream_mix_kernel<<<grid, 256, 0, e->stream>>>(P, (size_t)doubles_per_plane); ce = cudaGetLastError(); }
+    if (ce == cudaSuccess) ce = cudaEventRecord(a, e->stream);
+    for (int i = 0; i < iters && ce == cudaSuccess; ++i) { stream_mix_kernel<<<grid, 256, 0, e->stream>>>(P, (size_t)doubles_per_plane); ce = cudaGetLastError(); }
+    if (ce == cudaSuccess) ce = cudaEventRecord(b, e->stream);
+    if (ce == cudaSuccess) ce = cudaEventSynchronize(b);
+    float ms = 0.f;
+    if (ce == cudaSuccess) ce = cudaEventElapsedTime(&ms, a, b);
+    if (a) cudaEventDestroy(a);
+    if (b) cudaEventDestroy(b);
+    release();
+    if (ce != cudaSuccess) { cudaGetLastError(); return fail(ce == cudaErrorMemoryAllocation ? PQB_ERR_ALLOC : PQB_ERR_CUDA, "pqb_stream_mix: %s", cudaGetErrorString(ce)); }
+    *ms_per_iter = ms / (float)iters;
+    return PQB_OK;
+}
+
 extern "C" int pqb_flush_l2(pqb_engine *e) {
     if (!e) return fail(PQB_ERR_INVALID, "pqb_flush_l2: NULL");
     int rc = set_dev(e);
