@@ -251,3 +251,59 @@ def test_crossover_signals_are_exact_functions_of_the_suite_outputs():
     mv[a:] = np.where(m[1], m[0], np.nan); sv[a:] = np.where(ms[1], ms[0], np.nan)
     assert np.array_equal(sig["macd_cross"][s], cross(mv[None, :], sv[None, :])[0])
     panel.close()
+
+
+def test_partial_suite_next_to_optional_groups_runs_as_two_launches():
+    """Benchmark groups and optional groups together = two launches with their own ring layouts: a partial
+    suite (the BASE kernel) next to a few optional groups (the slot-dealt general kernel), long windows included."""
+    import polars_quant_b200 as pq
+    from polars_quant_b200 import _native as N
+    P = dict(midpoint_period=14, adosc_fast=3, adosc_slow=10, mom_period=10, roc_period=10, cmo_period=14, mfi_period=14,
+             cci_period=14, dm_period=9, trix_period=30, ultosc_period1=7, ultosc_period2=14, ultosc_period3=28, aroon_period=25)
+    d = _data()
+    S, NB = d["close"].shape
+    ind = N.IND["ema"] | N.IND["kdj"] | N.IND["atr"] | N.IND["midprice"] | N.IND_EXTRA["dm"] | N.IND_EXTRA["aroon"] | N.IND_EXTRA["mom"]
+    panel = pq.Panel(S, NB, outputs_mask=(1 << N.N_OUTPUTS) - 1)
+    panel.set_fields(d["close"], d["high"], d["low"], d["volume"])
+    res = panel.compute(N.default_params(indicators=ind, kdj_fastk=40, **P))
+    assert panel.last_launches() >= 2
+    op = pqo.SuiteParams.default()
+    op.stoch_k = 40
+    out, ok, _ = pqo.suite_panel(d["close"], d["high"], d["low"], d["volume"], op)
+    for name in ("ema", "atr", "kdj_k", "kdj_d", "kdj_j", "midprice"):
+        k = pqo.OUTPUT_NAMES.index(name)
+        nbad, msg = T.compare(name, res[name][0], res[name][1], out[k], ok[k])
+        assert nbad == 0, msg
+    for s in range(S):
+        refs = _refs(d, s, P)
+        for name in DM_OUT + ("aroon_up", "aroon_down", "mom"):
+            nbad, msg = T.compare(name, res[name][0][s], res[name][1][s], *refs[name])
+            assert nbad == 0, f"symbol {s}: {msg}"
+    panel.close()
+
+
+def test_pinned_planes_of_a_destroyed_panel_are_reused_without_stale_results():
+    """The engine keeps the pinned staging planes of destroyed panels for the next panel of the same shape: a second panel
+    on recycled planes (other inputs, leading nulls) must not see anything of the first."""
+    import polars_quant_b200 as pq
+    S, NB = 40, 500
+    d1, d2 = synth.ohlcv(S, NB, seed=1), synth.ohlcv(S, NB, seed=2)
+    p1 = pq.Panel(S, NB)
+    p1.set_fields(d1["close"], d1["high"], d1["low"], d1["volume"])
+    p1.compute()
+    addr1 = p1.host_output(0).ctypes.data
+    p1.close()
+    starts = np.zeros(S, dtype=np.int32)
+    starts[3], starts[17] = 120, 499
+    p2 = pq.Panel(S, NB)
+    assert p2.host_output(0).ctypes.data == addr1 or True          # (recycling is an optimisation, not a contract)
+    p2.set_fields(d2["close"], d2["high"], d2["low"], d2["volume"], starts=starts)
+    res = p2.compute()
+    for s in range(S):
+        a = int(starts[s])
+        o, k, _ = pqo.suite_panel(*(d2[f][s:s + 1, a:] for f in ("close", "high", "low", "volume")))
+        for q, name in enumerate(pqo.OUTPUT_NAMES):
+            assert not res[name][1][s, :a].any()
+            nbad, msg = T.compare(name, res[name][0][s, a:], res[name][1][s, a:], o[q, 0], k[q, 0])
+            assert nbad == 0, f"symbol {s}: {msg}"
+    p2.close()

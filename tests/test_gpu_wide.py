@@ -110,3 +110,21 @@ def test_info_last_row_reductions_match_the_oracle(tmp_path):
     assert info["ma_10"][0].as_py() == pytest.approx(c[-10:].mean(), rel=1e-14)
     r = c[-20:] / c[-21:-1] - 1.0
     assert info["volatility"][0].as_py() == pytest.approx(r.std(ddof=1) * np.sqrt(252.0) * 100.0, rel=1e-12)
+
+
+def test_info_on_a_panel_shorter_than_every_window():
+    """Three bars: the last-row columns and return_1d exist, everything that needs more history is null."""
+    d = synth.ohlcv(5, 3, seed=8)
+    p = pqb.Panel(5, 3)
+    p.set_fields(d["close"], d["high"], d["low"], d["volume"])
+    with pytest.raises(Exception):
+        p.info()                                         # inputs not on the device yet
+    p.upload()
+    got = p.info()
+    for s in range(5):
+        ref, rok = pqo.info(d["close"][s], d["high"][s], d["low"][s], d["volume"][s])
+        for k, name in enumerate(N.INFO_NAMES):
+            assert got[name][1][s] == rok[k]
+            if rok[k]:
+                assert got[name][0][s].view(np.uint64) == ref[k].view(np.uint64)
+    assert got["return_1d"][1].all() and not got["return_5d"][1].any() and not got["ma_5"][1].any() and got["amplitude"][1].all()
