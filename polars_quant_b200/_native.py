@@ -11,19 +11,21 @@ _PKG = Path(__file__).resolve().parent
 LIB_PATH = Path(os.environ["PQB_LIB"]) if os.environ.get("PQB_LIB") else _PKG / "libpqb200.so"
 
 N_FIELDS = 4
-N_OUTPUTS = 41
+N_OUTPUTS = 43
 N_SUITE_OUTPUTS = 21      # the 15-indicator benchmark suite; 21.. = optional groups
 CLOSE, HIGH, LOW, VOLUME = 0, 1, 2, 3
 OUTPUT_NAMES = ["sma", "ema", "tema", "trima", "bb_upper", "bb_middle", "bb_lower", "macd",
                 "macd_signal", "macd_hist", "rsi", "trange", "atr", "natr", "obv", "ad",
                 "kdj_k", "kdj_d", "kdj_j", "willr", "midprice",
                 "midpoint", "adosc", "mom", "roc", "rocp", "rocr", "rocr100", "cmo", "mfi", "cci",
-                "plus_dm", "minus_dm", "dx", "minus_di", "adx", "adxr", "trix", "ultosc", "aroon_up", "aroon_down"]
+                "plus_dm", "minus_dm", "dx", "minus_di", "adx", "adxr", "trix", "ultosc", "aroon_up", "aroon_down",
+                "donchian_upper", "donchian_lower"]
 IND = {"sma": 1 << 0, "ema": 1 << 1, "tema": 1 << 2, "trima": 1 << 3, "bbands": 1 << 4, "macd": 1 << 5,
        "rsi": 1 << 6, "trange": 1 << 7, "atr": 1 << 8, "natr": 1 << 9, "obv": 1 << 10, "ad": 1 << 11,
        "kdj": 1 << 12, "willr": 1 << 13, "midprice": 1 << 14}
 IND_EXTRA = {"midpoint": 1 << 15, "adosc": 1 << 16, "mom": 1 << 17, "roc": 1 << 18, "cmo": 1 << 19, "mfi": 1 << 20,
-             "cci": 1 << 21, "dm": 1 << 22, "trix": 1 << 23, "ultosc": 1 << 24, "aroon": 1 << 25}
+             "cci": 1 << 21, "dm": 1 << 22, "trix": 1 << 23, "ultosc": 1 << 24, "aroon": 1 << 25,
+             "donchian": 1 << 26}
 IND_ALL = (1 << 15) - 1
 
 ERR_NAMES = {-1: "PQB_ERR_NO_DEVICE", -2: "PQB_ERR_CUDA", -3: "PQB_ERR_INVALID", -4: "PQB_ERR_UNSUPPORTED",
@@ -47,7 +49,7 @@ class SuiteParams(C.Structure):
                 ("adosc_slow", C.c_int32), ("mom_period", C.c_int32), ("roc_period", C.c_int32),
                 ("cmo_period", C.c_int32), ("mfi_period", C.c_int32), ("cci_period", C.c_int32), ("dm_period", C.c_int32),
                 ("trix_period", C.c_int32), ("ultosc_period1", C.c_int32), ("ultosc_period2", C.c_int32),
-                ("ultosc_period3", C.c_int32), ("aroon_period", C.c_int32)]
+                ("ultosc_period3", C.c_int32), ("aroon_period", C.c_int32), ("donchian_period", C.c_int32)]
 
 
 class CandleParams(C.Structure):
@@ -125,6 +127,7 @@ def lib() -> C.CDLL:
                                           C.POINTER(C.c_float)]
         L.pqb_flush_l2.argtypes = [C.c_void_p]
         L.pqb_stream_mix.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_int, C.POINTER(C.c_float)]
+        L.pqb_donchian.argtypes = [C.c_void_p, C.POINTER(Col), C.POINTER(Col), C.c_int32, C.POINTER(OutCol), C.POINTER(OutCol)]
         L.pqb_dm.argtypes = [C.c_void_p, C.POINTER(Col), C.POINTER(Col), C.POINTER(Col), C.c_int32] + [C.POINTER(OutCol)] * 6
         L.pqb_selftest_divsqrt.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_uint64)]
         L.pqb_multi_destroy.argtypes = [C.c_void_p]

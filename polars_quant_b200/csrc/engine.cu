@@ -74,6 +74,7 @@ extern "C" void pqb_suite_params_default(pqb_suite_params *p) {
     p->midpoint_period = 14; p->adosc_fast = 3; p->adosc_slow = 10; p->mom_period = 10; p->roc_period = 10;
     p->cmo_period = 14; p->mfi_period = 14; p->cci_period = 14; p->dm_period = 14;
     p->trix_period = 30; p->ultosc_period1 = 7; p->ultosc_period2 = 14; p->ultosc_period3 = 28; p->aroon_period = 14;
+    p->donchian_period = 20;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -587,6 +588,11 @@ struct Built {
     int lead[PQB_N_OUTPUTS];   // first valid index of each output relative to the symbol start
 };
 
+static bool split_launch_enabled() {
+    const char *s = getenv("PQB_SPLIT_LAUNCH");           // (0: one general launch for everything -- measurement knob)
+    return !s || atoi(s) != 0;
+}
+
 // shared-memory ring layout of one launch: offsets of every enabled group's rings / van Herk arrays and the dynamic
 // shared-memory size (depends on A.gmask and the periods only, so a launch of a subset of the groups gets its own)
 static int layout_rings(SuiteArgs &A, const pqb_panel *p) {
@@ -621,6 +627,7 @@ retry_layout:
     A.off_adx = take((A.gmask & G_DM) ? A.dm_p - 1 : 0);
     A.off_ult = take((A.gmask & G_ULTOSC) ? 2 * std::max(std::max(A.ult_p1, A.ult_p2), A.ult_p3) : 2);
     A.off_arh = take((A.gmask & G_AROON) ? A.aroon_p + 1 : 0); A.off_arl = take((A.gmask & G_AROON) ? A.aroon_p + 1 : 0);
+    A.off_dh = take((A.gmask & G_DONCHIAN) ? A.don_p + 1 : 0); A.off_dl = take((A.gmask & G_DONCHIAN) ? A.don_p + 1 : 0);
     const long long smem = (long long)kFixedSmem + off * 8;
     if (smem > kMaxSmem && A.mid_own && mid_shares) { A.mid_own = 0; goto retry_layout; }   // long windows: share after all
     if (smem > kMaxSmem)
@@ -636,8 +643,8 @@ static void derive_roles(SuiteArgs &A) {
     A.roles = 0; A.n_roles = 0; A.fields = 0;
     for (int r = 0; r < N_ROLES; ++r)
         if (A.gmask & ROLE_GROUPS[r]) { A.roles |= 1u << r; ++A.n_roles; }
-    if (A.gmask & ~(unsigned)G_MIDPRICE) A.fields |= F_C;                     // everything but midprice reads close
-    if (A.gmask & (G_TRANGE | G_ATR | G_NATR | G_AD | G_KDJ | G_WILLR | G_MIDPRICE | G_ADOSC | G_MFI | G_CCI | G_DM | G_ULTOSC | G_AROON)) A.fields |= F_H | F_L;
+    if (A.gmask & ~(unsigned)(G_MIDPRICE | G_DONCHIAN)) A.fields |= F_C;        // everything but midprice / donchian reads close
+    if (A.gmask & (G_TRANGE | G_ATR | G_NATR | G_AD | G_KDJ | G_WILLR | G_MIDPRICE | G_ADOSC | G_MFI | G_CCI | G_DM | G_ULTOSC | G_AROON | G_DONCHIAN)) A.fields |= F_H | F_L;
     if (A.gmask & (G_OBV | G_AD | G_ADOSC | G_MFI)) A.fields |= F_V;
 }
 
@@ -843,6 +850,11 @@ static int build_args(const pqb_panel *p, const pqb_suite_params *sp, Built *out
         A.gmask |= G_AROON; A.aroon_p = sp->aroon_period; A.aroon_pd = (double)sp->aroon_period;
         bind_dyn(PQB_OUT_AROON_UP); bind_dyn(PQB_OUT_AROON_DOWN); upto((long long)sp->aroon_period + 1);
     }
+    if (ind & PQB_IND_DONCHIAN) {
+        if (sp->donchian_period <= 0) return fail(PQB_ERR_UNSUPPORTED, "donchian period %d <= 0 (a never-expiring window) is not built", sp->donchian_period);
+        A.gmask |= G_DONCHIAN; A.don_p = sp->donchian_period;
+        bind_dyn(PQB_OUT_DONCHIAN_UPPER); bind_dyn(PQB_OUT_DONCHIAN_LOWER);
+    }
     for (int k = PQB_N_SUITE_OUTPUTS; k < PQB_N_OUTPUTS; ++k)
         if (A.out[k] && !p->d_ovm[k]) return fail(PQB_ERR_INVALID, "internal: validity words of output %d are not allocated", k);
     A.steady_lead = steady;
@@ -850,6 +862,18 @@ static int build_args(const pqb_panel *p, const pqb_suite_params *sp, Built *out
     // roles with work, planes to stage
     derive_roles(A);
 
+    // benchmark groups next to optional groups run as two launches, each with its own layout (launch_suite): what has to
+    // fit is each half, not their union (e.g. WILLR(250) + MIDPRICE(250) next to DONCHIAN(250))
+    const unsigned gb = A.gmask & (unsigned)G_ALL, go = A.gmask & ~(unsigned)G_ALL;
+    if (gb && go && !A.vmask && split_launch_enabled()) {
+        for (unsigned part : {gb, go}) {
+            SuiteArgs t = A;
+            t.gmask = part;
+            if ((rc = layout_rings(t, p))) return rc;
+        }
+        A.smem_bytes = 0;                                   // (launch_suite lays each half out again)
+        return PQB_OK;
+    }
     return layout_rings(A, p);
 }
 
@@ -892,6 +916,7 @@ static uint64_t outputs_of_groups(unsigned g) {
     if (g & G_TRIX) m |= 1ull << 37;
     if (g & G_ULTOSC) m |= 1ull << 38;
     if (g & G_AROON) m |= 3ull << 39;
+    if (g & G_DONCHIAN) m |= 3ull << 41;
     return m;
 }
 
@@ -966,9 +991,8 @@ static int launch_suite(pqb_panel *p, const Built &full, int64_t b0, int64_t nb,
         // (it re-reads the input planes; the general kernel is 2.4x slower on the benchmark groups than the full-suite
         // kernel: 50,000 x 5,040 suite + MOM 23.2 ms in one general launch).  Null-aware mode has one kernel for everything.
         const unsigned gb = full.a.gmask & (unsigned)G_ALL, go = full.a.gmask & ~(unsigned)G_ALL;
-        const char *sp2 = getenv("PQB_SPLIT_LAUNCH");
         int rc;
-        if (gb && go && !full.a.vmask && (!sp2 || atoi(sp2) != 0)) {
+        if (gb && go && !full.a.vmask && split_launch_enabled()) {
             SuiteArgs ab = full.a, ao = full.a;
             ab.gmask = gb;
             ao.gmask = go;
@@ -1624,6 +1648,12 @@ extern "C" int pqb_aroon(pqb_engine *e, const pqb_col *h, const pqb_col *l, int3
     pqb_suite_params sp = only(PQB_IND_AROON); sp.aroon_period = tp;
     const pqb_col *c[] = {h, l}; const int f[] = {PQB_HIGH, PQB_LOW};
     const int o[] = {PQB_OUT_AROON_UP, PQB_OUT_AROON_DOWN}; pqb_out_col *d[] = {up, down};
+    return run_single(e, c, f, 2, NP_ERR, &sp, o, d, 2);
+}
+extern "C" int pqb_donchian(pqb_engine *e, const pqb_col *h, const pqb_col *l, int32_t tp, pqb_out_col *upper, pqb_out_col *lower) {
+    pqb_suite_params sp = only(PQB_IND_DONCHIAN); sp.donchian_period = tp;
+    const pqb_col *c[] = {h, l}; const int f[] = {PQB_HIGH, PQB_LOW};
+    const int o[] = {PQB_OUT_DONCHIAN_UPPER, PQB_OUT_DONCHIAN_LOWER}; pqb_out_col *d[] = {upper, lower};
     return run_single(e, c, f, 2, NP_ERR, &sp, o, d, 2);
 }
 extern "C" int pqb_dm(pqb_engine *e, const pqb_col *h, const pqb_col *l, const pqb_col *cl, int32_t tp, pqb_out_col *plus_dm,

@@ -45,8 +45,8 @@ def kernel_rec(tag, S, NB, ms, bps, **extra):
 if "groups" in which:
     # bytes per symbol-bar: 8 x (input planes the groups read + outputs they write); the suite + optional groups run as
     # two launches that both read their inputs
-    OUTS = {"midpoint": 1, "adosc": 1, "mom": 1, "roc": 4, "cmo": 1, "mfi": 1, "cci": 1, "dm": 6, "trix": 1, "ultosc": 1, "aroon": 2}
-    INS = {"midpoint": 1, "adosc": 4, "mom": 1, "roc": 1, "cmo": 1, "mfi": 4, "cci": 3, "dm": 3, "trix": 1, "ultosc": 3, "aroon": 2}
+    OUTS = {"midpoint": 1, "adosc": 1, "mom": 1, "roc": 4, "cmo": 1, "mfi": 1, "cci": 1, "dm": 6, "trix": 1, "ultosc": 1, "aroon": 2, "donchian": 2}
+    INS = {"midpoint": 1, "adosc": 4, "mom": 1, "roc": 1, "cmo": 1, "mfi": 4, "cci": 3, "dm": 3, "trix": 1, "ultosc": 3, "aroon": 2, "donchian": 2}
     for S in (10_000, 50_000):
         NB = 5_040
         p = pq.Panel(S, NB, engine=eng, outputs_mask=(1 << N.N_OUTPUTS) - 1, host_staging=False)
@@ -61,7 +61,7 @@ if "groups" in which:
         kernel_rec("suite + MOM (two launches)", S, NB, fused / 3, 200 + 16)
         allg = N.IND_ALL | sum(N.IND_EXTRA.values())
         tot, fused, nl = p.time_device(N.default_params(indicators=allg), warmup=1, iters=3)
-        kernel_rec("every group: 41 outputs (two launches)", S, NB, fused / 3, 8 * (4 + 21) + 8 * (4 + 20))
+        kernel_rec("every group: %d outputs (two launches)" % N.N_OUTPUTS, S, NB, fused / 3, 8 * (4 + 21) + 8 * (4 + N.N_OUTPUTS - 21))
         p.close()
 
 if "signals" in which:

@@ -22,7 +22,9 @@ def _refs(d, s, P):
     c, h, l, v = (d[f][s] for f in ("close", "high", "low", "volume"))
     dm = pqo.dm(h, l, c, P.get("dm_period", 14))             # calc_dm family, momentum.rs:668-727
     au, ad_ = pqo.aroon(h, l, P.get("aroon_period", 14))
+    du, dl = pqo.donchian(h, l, P.get("donchian_period", 20))    # SURVEY.md D3 (BASELINE config 5)
     return {
+        "donchian_upper": du, "donchian_lower": dl,
         **dm,
         "trix": pqo.trix(c, P.get("trix_period", 30)),
         "ultosc": pqo.ultosc(h, l, c, P.get("ultosc_period1", 7), P.get("ultosc_period2", 14), P.get("ultosc_period3", 28)),
@@ -51,10 +53,10 @@ def _data():
 
 @pytest.mark.parametrize("periods", [dict(), dict(midpoint_period=5, adosc_fast=2, adosc_slow=7, mom_period=1, roc_period=3,
                                                   cmo_period=1, mfi_period=2, cci_period=1, dm_period=1,
-                                                  trix_period=1, ultosc_period1=1, ultosc_period2=2, ultosc_period3=3, aroon_period=1),
+                                                  trix_period=1, ultosc_period1=1, ultosc_period2=2, ultosc_period3=3, aroon_period=1, donchian_period=1),
                                      dict(midpoint_period=60, adosc_fast=30, adosc_slow=12, mom_period=55, roc_period=41,
                                           cmo_period=33, mfi_period=29, cci_period=47, dm_period=37,
-                                          trix_period=21, ultosc_period1=12, ultosc_period2=9, ultosc_period3=20, aroon_period=21)])
+                                          trix_period=21, ultosc_period1=12, ultosc_period2=9, ultosc_period3=20, aroon_period=21, donchian_period=55)])
 def test_optional_groups_alone_and_with_the_suite(periods):
     import polars_quant_b200 as pq
     from polars_quant_b200 import _native as N
@@ -81,7 +83,8 @@ def test_optional_groups_alone_and_with_the_suite(periods):
     for g, bit in N.IND_EXTRA.items():
         res = panel.compute(N.default_params(indicators=bit, **P))
         names = (("roc", "rocp", "rocr", "rocr100") if g == "roc" else DM_OUT if g == "dm"
-                 else ("aroon_up", "aroon_down") if g == "aroon" else (g,))
+                 else ("aroon_up", "aroon_down") if g == "aroon"
+                 else ("donchian_upper", "donchian_lower") if g == "donchian" else (g,))
         for s in (0, 5, 6, 7, 8, 36):
             refs = _refs(d, s, P)
             for name in names:
@@ -140,6 +143,16 @@ def test_optional_single_column_entry_points():
     assert T.compare("mfi", *got(), *pqo.mfi(h, l, c, v, 14))[0] == 0
     N.check(L.pqb_cci(eng._h, C.byref(ch), C.byref(cl), C.byref(cc), 14, C.byref(oc)))
     assert T.compare("cci", *got(), *pqo.cci(h, l, c, 14))[0] == 0
+    # Donchian channel: two outputs, no warm-up nulls; its mid line is pqb_midprice
+    lo_v, lo_b = np.empty(n), np.zeros((n + 7) // 8, np.uint8)
+    oc2 = N.OutCol(lo_v.ctypes.data, lo_b.ctypes.data)
+    for p in (1, 20, 250):
+        N.check(L.pqb_donchian(eng._h, C.byref(ch), C.byref(cl), p, C.byref(oc), C.byref(oc2)))
+        up, lo = pqo.donchian(h, l, p)
+        assert T.compare("donchian_upper", *got(), *up)[0] == 0
+        assert T.compare("donchian_lower", lo_v, np.unpackbits(lo_b, bitorder="little")[:n].astype(bool), *lo)[0] == 0
+        assert got()[1].all()
+    assert L.pqb_donchian(eng._h, C.byref(ch), C.byref(cl), 0, C.byref(oc), C.byref(oc2)) == -4
 
 
 def test_directional_movement_family_quirks_and_plugin_names():

@@ -253,6 +253,7 @@ def test_config5_long_windows_kdj_donchian_atr(pq):
     d = synth.ohlcv(S, NB, seed=55)
     names = ("atr", "kdj_k", "kdj_d", "kdj_j", "willr", "midprice")
     omask = sum(1 << pqo.OUTPUT_NAMES.index(o) for o in names)
+    omask |= sum(1 << N.OUTPUT_NAMES.index(o) for o in ("donchian_upper", "donchian_lower"))
     panel = pq.Panel(S, NB, outputs_mask=omask)
     panel.set_fields(d["close"], d["high"], d["low"], d["volume"])
     pick = list(range(0, S, 37))
@@ -267,8 +268,8 @@ def test_config5_long_windows_kdj_donchian_atr(pq):
             nbad, msg = T.compare("atr", res["atr"][0][s], res["atr"][1][s], v, kk)
             assert nbad == 0, msg
     for p in (5, 20, 55, 250):
-        res = panel.compute(N.default_params(indicators=N.IND["willr"] | N.IND["midprice"], willr_period=p,
-                                             midprice_period=p))
+        res = panel.compute(N.default_params(indicators=N.IND["willr"] | N.IND["midprice"] | N.IND_EXTRA["donchian"],
+                                             willr_period=p, midprice_period=p, donchian_period=p))
         for s in pick:
             v, kk = pqo.willr(d["high"][s], d["low"][s], d["close"][s], p)
             nbad, msg = T.compare("willr", res["willr"][0][s], res["willr"][1][s], v, kk)
@@ -276,8 +277,11 @@ def test_config5_long_windows_kdj_donchian_atr(pq):
             v, kk = pqo.midprice(d["high"][s], d["low"][s], p)
             nbad, msg = T.compare("midprice", res["midprice"][0][s], res["midprice"][1][s], v, kk)
             assert nbad == 0, f"midprice {p} symbol {s}: {msg}"
-            up, lo = pqo.donchian(d["high"][s], d["low"][s], p)          # Donchian mid == midprice
+            up, lo = pqo.donchian(d["high"][s], d["low"][s], p)          # Donchian channel (D3); its mid == midprice
             assert T.same_bits((up[0] + lo[0]) / 2.0, res["midprice"][0][s]).all()
+            for name, (v, kk) in (("donchian_upper", up), ("donchian_lower", lo)):
+                nbad, msg = T.compare(name, res[name][0][s], res[name][1][s], v, kk)
+                assert nbad == 0, f"{name} {p} symbol {s}: {msg}"
     # two different 250-bar windows in one launch exceed the shared-memory budget: loud, not silent
     with pytest.raises(N.PqbError) as ei:
         panel.compute(N.default_params(indicators=N.IND["willr"] | N.IND["midprice"] | N.IND["kdj"], willr_period=250,
