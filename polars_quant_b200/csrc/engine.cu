@@ -675,6 +675,7 @@ static int build_args(const pqb_panel *p, const pqb_suite_params *sp, Built *out
 
     for (int f = 0; f < PQB_N_FIELDS; ++f) A.in[f] = p->d_in[f];
     for (int k = 0; k < PQB_N_OUTPUTS; ++k) { A.out[k] = nullptr; out->lead[k] = NEVER; }
+    A.don_fold = 0; A.don_p = 1;
     A.start = (p->starts_nonzero && !p->nulls_mode) ? p->d_start : nullptr;
     A.vmask = p->nulls_mode ? p->d_vmask : nullptr;
     A.symflags = p->nulls_mode ? p->d_flags : nullptr;
@@ -852,7 +853,11 @@ static int build_args(const pqb_panel *p, const pqb_suite_params *sp, Built *out
     }
     if (ind & PQB_IND_DONCHIAN) {
         if (sp->donchian_period <= 0) return fail(PQB_ERR_UNSUPPORTED, "donchian period %d <= 0 (a never-expiring window) is not built", sp->donchian_period);
-        A.gmask |= G_DONCHIAN; A.don_p = sp->donchian_period;
+        // next to a MIDPRICE of the same period in a partial suite the two lines are by-products of its window extremes
+        // (one launch, no second pass over high / low); otherwise a group of its own in the optional launch
+        A.don_p = sp->donchian_period;
+        if ((A.gmask & G_MIDPRICE) && A.mid_p == A.don_p && (A.gmask & (unsigned)G_ALL) != (unsigned)G_ALL) A.don_fold = 1;
+        else A.gmask |= G_DONCHIAN;
         bind_dyn(PQB_OUT_DONCHIAN_UPPER); bind_dyn(PQB_OUT_DONCHIAN_LOWER);
     }
     for (int k = PQB_N_SUITE_OUTPUTS; k < PQB_N_OUTPUTS; ++k)
@@ -925,7 +930,7 @@ static int launch_suite(pqb_panel *p, const Built &full, int64_t b0, int64_t nb,
                         int *launches) {
     pqb_engine *e = p->e;
     int n_launch = 0;
-    const uint64_t stored = outputs_of_groups(full.a.gmask);
+    const uint64_t stored = outputs_of_groups(full.a.gmask) | (full.a.don_fold ? 3ull << 41 : 0);
     const size_t boff = (size_t)b0 * p->bars_padded * SYM, bn = (size_t)nb * p->bars_padded * SYM;
     for (int k = 0; k < PQB_N_OUTPUTS; ++k) {
         if (full.a.out[k] && !(stored >> k & 1)) {

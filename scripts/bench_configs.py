@@ -3,7 +3,7 @@
 C3: 500 symbols x 1,000,000 minute bars, EMA(p) + MACD(12,26,9) per launch, p in 12/26/200/5000 (algorithmic
     bytes per launch: 1 in + 4 out = 40 B per symbol-bar).
 C5: 10,000 x 5,040, one launch per window: KDJ(k)+ATR(14) for k in 5/9/14/60/250 (3 in + 4 out = 56 B) and
-    WILLR(p)+MIDPRICE(p) for p in 5/20/55/250 (3 in + 2 out = 40 B)."""
+    WILLR(p)+MIDPRICE(p) for p in 5/20/55/250 (3 in + 2 out = 40 B), and the same + the Donchian channel's upper / lower."""
 import json, sys
 from pathlib import Path
 ROOT = Path(__file__).resolve().parents[1]
@@ -58,13 +58,16 @@ if "c3" in which:
         sp.close()
 if "c5" in which:
     S, NB = 10_000, 5_040
-    om = sum(1 << NAMES.index(o) for o in ("atr", "kdj_k", "kdj_d", "kdj_j", "willr", "midprice"))
+    om = sum(1 << NAMES.index(o) for o in ("atr", "kdj_k", "kdj_d", "kdj_j", "willr", "midprice", "donchian_upper", "donchian_lower"))
     p = pq.Panel(S, NB, engine=eng, outputs_mask=om, host_staging=False)
     p.fill_synthetic(seed=55, sigma=0.02)
     for k in (5, 9, 14, 60, 250):
         run(f"c5 kdj({k},3,3)+atr(14)", p, N.default_params(indicators=N.IND["kdj"] | N.IND["atr"], kdj_fastk=k), 56, S, NB)
     for w in (5, 20, 55, 250):
         run(f"c5 willr({w})+midprice({w})", p, N.default_params(indicators=N.IND["willr"] | N.IND["midprice"], willr_period=w, midprice_period=w), 40, S, NB)
+    for w in (5, 20, 55, 250):      # + the Donchian channel's upper / lower lines (a second launch: optional group; 2 in + 2 out more)
+        run(f"c5 willr({w})+midprice({w})+donchian({w})", p, N.default_params(indicators=N.IND["willr"] | N.IND["midprice"] | N.IND_EXTRA["donchian"],
+            willr_period=w, midprice_period=w, donchian_period=w), 40 + 32, S, NB)
     p.close()
 if "--json" in sys.argv:
     Path(sys.argv[sys.argv.index("--json") + 1]).write_text(json.dumps(out, indent=1))
