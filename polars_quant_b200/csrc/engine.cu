@@ -81,6 +81,7 @@ extern "C" void pqb_suite_params_default(pqb_suite_params *p) {
 // engine / panel objects
 // ---------------------------------------------------------------------------------------
 static constexpr int kMaxSmem = 227 * 1024;      // opt-in dynamic shared memory per CTA on sm_100
+static constexpr int kSmemThreeCtas = 75 * 1024; // (228 KB per SM - 1 KB reserved per CTA) / 3
 static constexpr int kFixedSmem = NS * STAGE_BYTES + 2 * NS * 8;   // TMA stages (+ validity words) + mbarriers
 
 struct pqb_engine {
@@ -600,8 +601,14 @@ static int layout_rings(SuiteArgs &A, const pqb_panel *p) {
     const bool mid_shares = (A.gmask & G_WILLR) && A.willr_p == A.mid_p;
     // MIDPRICE shares WILLR's arrays when the windows are equal -- except for the full suite on a small panel, where the
     // nine-warp variant runs it in a warp of its own (launch_suite picks that variant only if these arrays exist)
+    // ... and for a partial suite in the latency regime (at most one wave of three CTAs per SM) with a role warp to spare,
+    // where deal_base_slots() gives WILLR and MIDPRICE a warp each
+    int active_roles = 0;
+    for (int r = 0; r < N_ROLES; ++r) active_roles += (A.gmask & ROLE_GROUPS[r]) ? 1 : 0;
+    const bool partial_spare = !(A.gmask & ~(unsigned)G_ALL) && A.gmask != (unsigned)G_ALL && active_roles < N_ROLES &&
+                               p->n_blocks <= 3ll * p->e->sm_count;
     A.mid_own = (A.gmask & G_MIDPRICE) &&
-                (!mid_shares || (A.gmask == G_ALL && p->n_blocks <= p->e->sm_count + p->e->sm_count / N_ROLES_X));
+                (!mid_shares || partial_spare || (A.gmask == G_ALL && p->n_blocks <= p->e->sm_count + p->e->sm_count / N_ROLES_X));
 retry_layout:
     long long off = 0;
     auto take = [&](int slots) { const long long o = off; off += (long long)std::max(slots, 1) * SYM; return (int)std::min<long long>(o, 1ll << 30); };
@@ -630,6 +637,7 @@ retry_layout:
     A.off_dh = take((A.gmask & G_DONCHIAN) ? A.don_p + 1 : 0); A.off_dl = take((A.gmask & G_DONCHIAN) ? A.don_p + 1 : 0);
     const long long smem = (long long)kFixedSmem + off * 8;
     if (smem > kMaxSmem && A.mid_own && mid_shares) { A.mid_own = 0; goto retry_layout; }   // long windows: share after all
+    if (smem > kSmemThreeCtas && A.mid_own && mid_shares && partial_spare) { A.mid_own = 0; goto retry_layout; }   // (not at the cost of a CTA per SM)
     if (smem > kMaxSmem)
         return fail(PQB_ERR_UNSUPPORTED,
                     "windows too long for one launch: the per-block rings need %lld bytes of shared memory (limit %d); "
@@ -925,6 +933,46 @@ static uint64_t outputs_of_groups(unsigned g) {
     return m;
 }
 
+// Partial suites: deal the seven role warps of the BASE kernel as (role, groups) slots.  Every active role gets a warp;
+// spare warps take one half of a two-part role -- WILLR | MIDPRICE (needs MIDPRICE's own arrays), OBV + TRIMA | AD,
+// EMA + TEMA | MACD + SMA, TRANGE + ATR | NATR -- so that a launch with few roles has shorter per-bar chains
+// (BASELINE config 5: WILLR + MIDPRICE in two warps instead of one).  A.roles / A.n_roles become the slots with work.
+static void deal_base_slots(SuiteArgs &A) {
+    static const int order[N_ROLES] = {1, 2, 0, 5, 3, 6, 4};             // warp order of the seven-role kernels
+    int n = 0;
+    for (int w = 0; w < N_ROLES; ++w) { A.slot_role[w] = 0; A.slot_mask[w] = 0; }
+    for (int i = 0; i < N_ROLES; ++i) {
+        const unsigned m = A.gmask & ROLE_GROUPS[order[i]];
+        if (m) { A.slot_role[n] = order[i]; A.slot_mask[n] = m; ++n; }
+    }
+    struct Cut { int role; unsigned half; };
+    const Cut cuts[] = {{6, (unsigned)(G_MIDPRICE)}, {4, (unsigned)G_AD}, {0, (unsigned)(G_MACD | G_SMA)}, {3, (unsigned)G_NATR}};
+    const char *ds = getenv("PQB_DEAL_SLOTS");
+    if (!ds || atoi(ds) != 0)
+        for (const Cut &c : cuts) {
+            if (n >= N_ROLES) break;
+            if (c.role == 6 && !A.mid_own) continue;
+            for (int w = 0; w < n; ++w) {
+                if (A.slot_role[w] != c.role) continue;
+                const unsigned a = A.slot_mask[w] & c.half, b = A.slot_mask[w] & ~c.half;
+                if (a && b) { A.slot_mask[w] = b; A.slot_role[n] = c.role; A.slot_mask[n] = a; ++n; }
+                break;
+            }
+        }
+    // role -> slot code: 3 * role, + 1 for the half without the cut groups, + 2 for the cut half
+    for (int w = 0; w < n; ++w) {
+        const int role = A.slot_role[w];
+        const unsigned whole = A.gmask & ROLE_GROUPS[role];
+        int part = 0;
+        if (A.slot_mask[w] != whole)
+            for (const Cut &c : cuts)
+                if (c.role == role) part = (A.slot_mask[w] & c.half) ? 2 : 1;
+        A.slot_role[w] = 3 * role + part;
+    }
+    A.roles = (1u << n) - 1;
+    A.n_roles = n;
+}
+
 // Launches the suite over symbol blocks [b0, b0+nb) (+ NaN fills + validity bitmaps of those symbols).
 static int launch_suite(pqb_panel *p, const Built &full, int64_t b0, int64_t nb, cudaEvent_t ev_after_fused,
                         int *launches) {
@@ -983,7 +1031,10 @@ static int launch_suite(pqb_panel *p, const Built &full, int64_t b0, int64_t nb,
         else if (small)
             suite_fused_kernel<true, false, false, true><<<grid, CTA_THREADS_X, a.smem_bytes, e->stream>>>(a);
         else if (fulls) suite_fused_kernel<true, false><<<grid, CTA_THREADS, a.smem_bytes, e->stream>>>(a);
-        else if (!(a.gmask & ~(unsigned)G_ALL)) suite_fused_kernel<false, false, true><<<grid, CTA_THREADS, a.smem_bytes, e->stream>>>(a);
+        else if (!(a.gmask & ~(unsigned)G_ALL)) {
+            deal_base_slots(a);
+            suite_fused_kernel<false, false, true><<<grid, CTA_THREADS, a.smem_bytes, e->stream>>>(a);
+        }
         else if (wide) suite_fused_kernel<false, false, false, true><<<grid, CTA_THREADS_W, a.smem_bytes, e->stream>>>(a);
         else suite_fused_kernel<false, false><<<grid, CTA_THREADS, a.smem_bytes, e->stream>>>(a);
         CU(cudaGetLastError());
