@@ -98,7 +98,11 @@ struct pqb_engine {
     int64_t cscratch_bars = 0;
     // pinned staging planes of destroyed panels, kept for the next panel of the same shape: page-locking is the
     // expensive part of creating a panel (measured: 0.48 s of a 0.9 s WidePanel.suite() call on 2,000 x 2,520)
-    std::mutex pool_mu;
+    // panels hold a pointer to their engine: pqb_engine_destroy() with panels still alive (a garbage collector finalising
+    // objects in any order) only marks the engine, and the last panel to go frees it
+    int live_panels = 0;
+    bool destroy_requested = false;
+    std::mutex pool_mu;                  // guards live_panels / destroy_requested / the pool
     std::multimap<size_t, void *> host_pool;
     size_t host_pool_bytes = 0, host_pool_cap = 4ull << 30;
 };
@@ -179,6 +183,9 @@ struct pqb_panel {
     // crossover signals (signals_host.inc): row-major int8 planes, allocated on first use
     int8_t *d_sig = nullptr, *h_sig = nullptr;
     bool inputs_resident = false;        // the tiled input planes hold the panel (upload / run_host / fill_synthetic)
+    bool retained = false;               // registered with the engine (engine_retain)
+    double *d_info = nullptr;            // last-row reductions (info_host.inc): [PQB_N_INFO][n_symbols] + validity bytes
+    uint8_t *d_info_valid = nullptr;
 };
 
 static int set_dev(const pqb_engine *e) {
@@ -226,17 +233,40 @@ extern "C" int pqb_engine_create(int device, pqb_engine **out) {
     return PQB_OK;
 }
 
-extern "C" void pqb_engine_destroy(pqb_engine *e) {
-    if (!e) return;
+static void engine_free(pqb_engine *e) {
     cudaSetDevice(e->device);
-    if (e->scratch) pqb_panel_destroy(e->scratch);
-    if (e->cscratch) pqb_candles_destroy(e->cscratch);
     for (auto &kv : e->host_pool) cudaFreeHost(kv.second);
     if (e->flush_buf) cudaFree(e->flush_buf);
     if (e->stream) cudaStreamDestroy(e->stream);
     if (e->h2d) cudaStreamDestroy(e->h2d);
     if (e->d2h) cudaStreamDestroy(e->d2h);
     delete e;
+}
+
+extern "C" void pqb_engine_destroy(pqb_engine *e) {
+    if (!e) return;
+    cudaSetDevice(e->device);
+    if (e->scratch) { pqb_panel_destroy(e->scratch); e->scratch = nullptr; }
+    if (e->cscratch) { pqb_candles_destroy(e->cscratch); e->cscratch = nullptr; }
+    {
+        std::lock_guard<std::mutex> lk(e->pool_mu);
+        if (e->live_panels > 0) { e->destroy_requested = true; return; }      // the last panel frees the engine
+    }
+    engine_free(e);
+}
+
+// a panel (suite or candle) registers with / leaves its engine
+static void engine_retain(pqb_engine *e) {
+    std::lock_guard<std::mutex> lk(e->pool_mu);
+    ++e->live_panels;
+}
+static void engine_release(pqb_engine *e) {
+    bool last;
+    {
+        std::lock_guard<std::mutex> lk(e->pool_mu);
+        last = --e->live_panels == 0 && e->destroy_requested;
+    }
+    if (last) engine_free(e);
 }
 
 extern "C" int pqb_panel_create(pqb_engine *e, int64_t n_symbols, int64_t n_bars, uint32_t fields_mask,
@@ -251,6 +281,8 @@ extern "C" int pqb_panel_create(pqb_engine *e, int64_t n_symbols, int64_t n_bars
     if (rc) return rc;
     pqb_panel *p = new pqb_panel();
     p->e = e;
+    engine_retain(e);
+    p->retained = true;
     p->n_symbols = n_symbols;
     p->n_bars = n_bars;
     p->pitch = (n_bars + 15) / 16 * 16;
@@ -332,6 +364,8 @@ extern "C" void pqb_panel_destroy(pqb_panel *p) {
     if (p->d_vmask) cudaFree(p->d_vmask);
     if (p->d_flags) cudaFree(p->d_flags);
     if (p->d_sig) cudaFree(p->d_sig);
+    if (p->d_info) cudaFree(p->d_info);
+    if (p->d_info_valid) cudaFree(p->d_info_valid);
     if (p->h_sig) cudaFreeHost(p->h_sig);
     const size_t hplane = (size_t)p->n_symbols * p->pitch * sizeof(double);
     const size_t bplane = (size_t)p->n_symbols * p->words_per_row * sizeof(uint32_t);
@@ -340,7 +374,9 @@ extern "C" void pqb_panel_destroy(pqb_panel *p) {
     for (auto &q : p->h_bits) host_give(p->e, q, bplane);
     for (auto &ev : p->ev_packed) if (ev) cudaEventDestroy(ev);
     for (auto &ev : p->ev_d2h) if (ev) cudaEventDestroy(ev);
+    pqb_engine *e = p->retained ? p->e : nullptr;
     delete p;
+    if (e) engine_release(e);
 }
 
 extern "C" int64_t pqb_panel_pitch(const pqb_panel *p) { return p ? p->pitch : 0; }

@@ -320,3 +320,21 @@ def test_pinned_planes_of_a_destroyed_panel_are_reused_without_stale_results():
             nbad, msg = T.compare(name, res[name][0][s, a:], res[name][1][s, a:], o[q, 0], k[q, 0])
             assert nbad == 0, f"symbol {s}: {msg}"
     p2.close()
+
+
+def test_engine_destroyed_before_its_panels_is_deferred():
+    """A garbage collector may finalise an engine before the panels that point to it (interpreter shutdown): the engine is
+    only marked then, the panels stay usable and the last one to go frees it (pinned planes go through the engine's pool)."""
+    import polars_quant_b200 as pq
+    from polars_quant_b200 import candles
+    eng = pq.Engine(0)
+    d = synth.ohlcv(8, 300, seed=4)
+    p = pq.Panel(8, 300, engine=eng)
+    cp = candles.CandlePanel(8, 300, engine=eng)
+    p.set_fields(d["close"], d["high"], d["low"], d["volume"])
+    eng.close()                                            # destroy requested while two panels are alive
+    res = p.compute()
+    out, ok, _ = pqo.suite_panel(d["close"], d["high"], d["low"], d["volume"])
+    assert not T.compare_all(res, out, ok, pqo.OUTPUT_NAMES)
+    p.close()
+    cp.close()                                             # last one out frees the engine
