@@ -426,3 +426,30 @@ def test_multi_gpu_driver_shards_by_symbol(pq):
             nbad, msg = T.compare(name, v, b, out[k][s], ok[k][s])
             assert nbad == 0, f"symbol {s}: {msg}"
     mp.close()
+
+
+@pytest.mark.parametrize("n_symbols", [70, 4736 + 96])
+def test_closes_at_the_window_extremes_keep_their_signed_zeros(pq, n_symbols):
+    """Real bars close at their high or low now and then: WILLR's and STOCH's numerators are then exactly 0 (and
+    -100 * 0 is -0.0): values and signs must equal the oracle bit for bit through the divisions' fast and slow paths --
+    plain kernel (70 symbols: three CTAs per SM) and the pipelined small-panel variant (151 blocks)."""
+    NB = 300
+    d = synth.ohlcv(n_symbols, NB, seed=77)
+    rng = np.random.default_rng(3)
+    m = rng.random((n_symbols, NB)) < 0.15
+    d["high"][m] = d["close"][m]
+    m = rng.random((n_symbols, NB)) < 0.15
+    d["low"][m] = d["close"][m]
+    _run_vs_oracle(pq, d)
+    names = ("willr", "kdj_k", "kdj_d", "kdj_j")                 # and as a partial suite (BASE kernel, pipelined roles)
+    panel = pq.Panel(n_symbols, NB, outputs_mask=sum(1 << pqo.OUTPUT_NAMES.index(o) for o in names))
+    panel.set_fields(d["close"], d["high"], d["low"], d["volume"])
+    from polars_quant_b200 import _native as N
+    res = panel.compute(N.default_params(indicators=N.IND["willr"] | N.IND["kdj"]))
+    out, ok = _oracle(d)
+    for name in names:
+        k = pqo.OUTPUT_NAMES.index(name)
+        nbad, msg = T.compare(name, res[name][0], res[name][1], out[k], ok[k])
+        assert nbad == 0, msg
+    assert (np.signbit(res["willr"][0]) & (res["willr"][0] == 0.0)).any()      # the -0.0 case occurs
+    panel.close()
