@@ -25,3 +25,11 @@ for frac in (0.02, 0.10):
     p.upload()
     tot, fused, nl = p.time_device(prm, warmup=2, iters=10)
     print(json.dumps({"config": "close == high on %.0f%% and close == low on %.0f%% of the bars" % (frac * 100, frac * 100), "kernel_ms": fused / 10}))
+# the same without any bar where high == low == close: only the highs touch
+p.fill_synthetic(seed=5, to_host=True)
+c, h = p.host_field("close"), p.host_field("high")
+m = rng.random((S, NB)) < 0.10
+h[:, :NB][m] = c[:, :NB][m]
+p.upload()
+tot, fused, nl = p.time_device(prm, warmup=2, iters=10)
+print(json.dumps({"config": "close == high on 10% of the bars, lows untouched", "kernel_ms": fused / 10}))
