@@ -11,12 +11,16 @@
  * operation order, `fma()` exactly where the Rust uses `mul_add`, plain un-contracted
  * arithmetic elsewhere (build with -ffp-contract=off, no fast-math).
  *
- * PARITY UNPINNED: the reference ships no tests, golden vectors or KATs for this path
- * (reference tests/__init__.py:1-4 is a scratch TA-Lib call), it cannot be compiled here
- * (no Rust toolchain; the snapshot has undefined symbols, e.g. calc_rma) and its binary is
- * absent.  The oracle is therefore pinned only against (a) an independent pure-Python
- * restatement written from the same Rust text (oracle/ref_py.py) and (b) the golden
- * vectors that restatement generated (tests/golden/, made by tests/golden/make_golden.py).
+ * PARITY PINNED TO THE REFERENCE'S OWN OUTPUTS (round 2).  The reference ships no tests, golden vectors or
+ * KATs for this path (its tests/__init__.py:1-4 is a scratch TA-Lib call) and cannot be compiled here (no Rust
+ * toolchain; the snapshot has undefined symbols, e.g. calc_rma).  Its functions are, however, plain scalar
+ * loops, so tests/golden/make_ref_golden.py EXECUTES the reference's source text (src/talib/*.rs through the
+ * small Rust-subset interpreter in tests/golden/rustexec/, python/polars_quant/talib/*.py imported verbatim)
+ * and commits the outputs as tests/golden/talib_ref_golden.npz; tests/test_oracle_ref_golden.py holds every
+ * function of this file to those vectors bit for bit (values, validity, and the inputs on which the reference
+ * returns Err or panics).  Still defined here rather than by the reference: D1-D3 below (the reference's own
+ * gaps).  The older vectors (tests/golden/talib_golden.npz, from the independent restatement oracle/ref_py.py)
+ * are kept as a second check.
  *
  * Column convention: `x` = values, `xok` = byte validity (1 = valid, 0 = null) or NULL for
  * "no validity bitmap / no nulls"; outputs `out` / `ok` likewise (ok never NULL).  A null
@@ -206,19 +210,145 @@ EXPORT int pqo_wma(const double *x, const uint8_t *xok, int64_t n, int64_t p,
     return PQO_OK;
 }
 
+/* ------------------------------------------------------------------ calc_dema (oracle-only)
+ * overlap.rs:543-658, LITERAL including its defects.  `ema_value` and `sum` are 2-slot ArrayVecs (:554-555).
+ * The bitmap branch (:560-602, taken by a chunk that carries a validity bitmap) is a DEMA whose first value
+ * appears at count == 2p (one bar late).  The no-bitmap branch (:603-654) is a pasted TEMA body: it indexes
+ * slot 2 of the 2-slot arrays (:625 and on) -> panic (= abort) as soon as count reaches 2p-1 (p == 1: at
+ * count 2, through the `_` arm).  `xok == NULL` selects the no-bitmap branch, like everywhere in this file. */
+EXPORT int pqo_dema(const double *x, const uint8_t *xok, int64_t n, int64_t p,
+                    double *out, uint8_t *ok) {
+    if (p <= 0 || n < 2 * p - 1) { all_null(out, ok, n); return PQO_OK; }   /* :546 */
+    double alpha = 2.0 / ((double)p + 1.0);
+    int64_t count = 0; double e[2] = {0, 0}, s[2] = {0, 0};
+    for (int64_t i = 0; i < n; ++i) {
+        if (!is_ok(xok, i)) { put_null(out, ok, i); continue; }
+        double value = x[i];
+        count += 1;
+        if (count < p) { s[0] += value; put_null(out, ok, i); }
+        else if (count == p) { s[0] += value; e[0] = s[0] / (double)p; s[1] = e[0]; put_null(out, ok, i); }
+        else if (count < 2 * p - 1) { e[0] = fma(alpha, value - e[0], e[0]); s[1] += e[0]; put_null(out, ok, i); }
+        else if (count == 2 * p - 1) {
+            e[0] = fma(alpha, value - e[0], e[0]); s[1] += e[0]; e[1] = s[1] / (double)p;
+            if (xok == NULL) return PQO_ERR_PANIC;                         /* :625 sum[2] = ... */
+            put_null(out, ok, i);
+        } else {
+            if (xok == NULL) return PQO_ERR_PANIC;                         /* :627-651: slot 2 again */
+            e[0] = fma(alpha, value - e[0], e[0]);
+            e[1] = fma(alpha, e[0] - e[1], e[1]);
+            put_val(out, ok, i, 2.0 * e[0] - e[1]);                        /* :597 */
+        }
+    }
+    return PQO_OK;
+}
+
+/* ------------------------------------------------------------------ calc_t3 (oracle-only)
+ * overlap.rs:939-1175, LITERAL.  Six cascaded EMAs; stage k accumulates while count < (k+1)p-k and is
+ * seeded at count == (k+1)p-k -- except the sixth (k = 5), which has no seeding arm (:1042-1057): it starts
+ * from 0.0 in the `_` arm.  The two branches end differently: the bitmap branch (:1058-1063) emits
+ * 6e0 - 15e1 + 20e2 - 15e3 + 6e4 - e5, the no-bitmap branch (:1160-1166) the nested mul_add of c1..c4 over
+ * e5..e2.  The arms are tried in source order (first match wins: matters for p == 1). */
+EXPORT int pqo_t3(const double *x, const uint8_t *xok, int64_t n, int64_t p, double vfactor,
+                  double *out, uint8_t *ok) {
+    if (p <= 0 || n < 6 * p - 5) { all_null(out, ok, n); return PQO_OK; }   /* :942 */
+    double alpha = 2.0 / ((double)p + 1.0);
+    double v3 = vfactor * vfactor * vfactor, v2 = vfactor * vfactor;          /* powi(3), powi(2) */
+    double c1 = -v3;                                                          /* :949 */
+    double c2 = 3.0 * v2 - 3.0 * c1;
+    double c3 = -2.0 * c2 - 3.0 * c1 - 3.0 * vfactor;
+    double c4 = 1.0 - c1 - c2 - c3;
+    int64_t count = 0; double e[6] = {0, 0, 0, 0, 0, 0}, s[6] = {0, 0, 0, 0, 0, 0};
+    for (int64_t i = 0; i < n; ++i) {
+        if (!is_ok(xok, i)) { put_null(out, ok, i); continue; }
+        double value = x[i];
+        count += 1;
+        int k, done = 0;
+        for (k = 0; k < 6 && !done; ++k) {
+            int64_t t = (int64_t)(k + 1) * p - k;
+            int acc = count < t, seed = (k < 5) && count == t;
+            if (!acc && !seed) continue;
+            for (int j = 0; j < k; ++j)                                       /* the stages already running */
+                e[j] = fma(alpha, (j == 0 ? value : e[j - 1]) - e[j], e[j]);
+            s[k] += (k == 0) ? value : e[k - 1];
+            if (seed) { e[k] = s[k] / (double)p; s[k + 1] = e[k]; }
+            put_null(out, ok, i);
+            done = 1;
+        }
+        if (done) continue;
+        for (int j = 0; j < 6; ++j)
+            e[j] = fma(alpha, (j == 0 ? value : e[j - 1]) - e[j], e[j]);
+        if (xok != NULL)
+            put_val(out, ok, i, 6.0 * e[0] - 15.0 * e[1] + 20.0 * e[2] - 15.0 * e[3] + 6.0 * e[4] - e[5]);
+        else
+            put_val(out, ok, i, fma(c1, e[5], fma(c2, e[4], fma(c3, e[3], c4 * e[2]))));
+    }
+    return PQO_OK;
+}
+
+/* ------------------------------------------------------------------ calc_kama (oracle-only)
+ * overlap.rs:732-855, LITERAL.  Pass 1 (:748-807): a non-standard efficiency ratio,
+ * er = |v - v[t-p]| / running sum of those same |v - v[t-p]| terms (window_sum), null for the first p values;
+ * `window_sum.pop_front().unwrap()` panics for p == 1.  Then sc = (er * (2/3 - 2/31) + 2/31)^2 with polars'
+ * null-propagating arithmetic (:811-815).  Pass 2 (:817-852) needs `values.cont_slice().unwrap()`: a column
+ * with nulls (or several chunks) panics; the first p non-null sc slots only accumulate the price (null), the
+ * next one emits sum/p WITHOUT using its own bar, afterwards kama = sc.mul_add(v - kama, kama). */
+EXPORT int pqo_kama(const double *x, const uint8_t *xok, int64_t n, int64_t p,
+                    double *out, uint8_t *ok) {
+    if (p <= 0 || n < p) { all_null(out, ok, n); return PQO_OK; }           /* :735 */
+    double *er = (double *)malloc(sizeof(double) * (size_t)(n + 1));
+    uint8_t *erok = (uint8_t *)malloc((size_t)(n + 1));
+    double *win = (double *)malloc(sizeof(double) * (size_t)(n + 1));       /* VecDeques as [head, tail) */
+    double *wsum = (double *)malloc(sizeof(double) * (size_t)(n + 1));
+    if (!er || !erok || !win || !wsum) { free(er); free(erok); free(win); free(wsum); return PQO_ERR_ALLOC; }
+    int64_t wh = 0, wt = 0, sh = 0, st = 0, count = 0;
+    double sum = 0.0, diff_abs;
+    int rc = PQO_OK;
+    for (int64_t i = 0; i < n && rc == PQO_OK; ++i) {
+        if (!is_ok(xok, i)) { er[i] = NAN; erok[i] = 0; continue; }
+        double value = x[i];
+        if (count == 0) { count += 1; win[wt++] = value; er[i] = NAN; erok[i] = 0; }
+        else if (count < p) {
+            count += 1;
+            diff_abs = fabs(value - win[wh]);                                  /* front() */
+            sum += diff_abs; win[wt++] = value; wsum[st++] = diff_abs;
+            er[i] = NAN; erok[i] = 0;
+        } else {
+            if (wh == wt || sh == st) { rc = PQO_ERR_PANIC; break; }           /* unwrap() on None */
+            diff_abs = fabs(value - win[wh++]);
+            sum += diff_abs - wsum[sh++];
+            win[wt++] = value; wsum[st++] = diff_abs;
+            er[i] = diff_abs / sum; erok[i] = 1;
+        }
+    }
+    if (rc == PQO_OK && has_nulls(xok, n)) rc = PQO_ERR_PANIC;                 /* :826 cont_slice().unwrap() */
+    if (rc == PQO_OK) {
+        double fast_sc = 2.0 / 3.0, slow_sc = 2.0 / 31.0;
+        double kama = 0.0; sum = 0.0; count = 0;
+        for (int64_t i = 0; i < n; ++i) {
+            if (!erok[i]) { put_null(out, ok, i); continue; }
+            double sc_sqrt = er[i] * (fast_sc - slow_sc) + slow_sc;
+            double sc = sc_sqrt * sc_sqrt;
+            if (count < p) { count += 1; sum += x[i]; put_null(out, ok, i); }
+            else if (count == p) { count += 1; kama = sum / (double)p; put_val(out, ok, i, kama); }
+            else { kama = fma(sc, x[i] - kama, kama); put_val(out, ok, i, kama); }
+        }
+    }
+    free(er); free(erok); free(win); free(wsum);
+    return rc;
+}
+
 /* ------------------------------------------------------------------ calc_ma
- * overlap.rs:857-869.  matype 3 (DEMA), 6 (KAMA), 8 (T3) are buggy in the reference
- *  and not restated: PQO_ERR_PANIC. */
+ * overlap.rs:857-869. */
 EXPORT int pqo_ma(const double *x, const uint8_t *xok, int64_t n, int64_t p, int64_t matype,
                   double *out, uint8_t *ok) {
     switch (matype) {
         case 1: return pqo_ema(x, xok, n, p, out, ok);
         case 2: return pqo_wma(x, xok, n, p, out, ok);
-        case 3: return PQO_ERR_PANIC;
+        case 3: return pqo_dema(x, xok, n, p, out, ok);
         case 4: return pqo_tema(x, xok, n, p, out, ok);
         case 5: return pqo_trima(x, xok, n, p, out, ok);
-        case 6: return PQO_ERR_PANIC;
-        case 8: return PQO_ERR_PANIC;
+        case 6: return pqo_kama(x, xok, n, p, out, ok);
+        case 8: return pqo_t3(x, xok, n, p, 0.0, out, ok);
         default: return pqo_sma(x, xok, n, p, out, ok);               /* 0, 7, other */
     }
 }
@@ -344,7 +474,10 @@ EXPORT int pqo_midprice(const double *high, const uint8_t *hok, const double *lo
     for (int64_t i = 0; i < n; ++i) {
         double value = low[i];
         count += 1;
-        while (w.len > 0 && w.val[dq_pos(&w, w.len - 1)] >= value) dq_pop_back(&w);
+        /* :363 the bitmap branch of the low pass compares with `<=` (a rolling MAX of low); :384 the no-bitmap
+         * branch with `>=`.  A low column that carries a validity bitmap, even an all-set one, takes the former. */
+        if (lok) { while (w.len > 0 && w.val[dq_pos(&w, w.len - 1)] <= value) dq_pop_back(&w); }
+        else     { while (w.len > 0 && w.val[dq_pos(&w, w.len - 1)] >= value) dq_pop_back(&w); }
         if (w.len > 0 && w.idx[w.head] == count - (uint64_t)p) dq_pop_front(&w);
         dq_push_back(&w, count, value);
         double lm = w.val[w.head];
@@ -736,6 +869,47 @@ EXPORT int pqo_stochf(const double *h, const uint8_t *hok, const double *l, cons
                       double *fastd, uint8_t *fastdok) {
     int rc = fastk_line(h, hok, l, lok, c, cok, n, fastk_period, fastk, fastkok);
     if (!rc) rc = pqo_ma(fastk, fastkok, n, fastd_period, fastd_matype, fastd, fastdok);
+    return rc;
+}
+/* STOCHRSI (momentum.py:197-205): the STOCHF construction over the RSI line itself:
+ * rsi = RSI(real, timeperiod); fastk = (rsi - rolling_min(rsi, k)) * 100 / (rolling_max(rsi, k) - rolling_min(rsi, k));
+ * fastd = MA(fastk, fastd_period, fastd_matype). */
+EXPORT int pqo_rsi(const double *x, const uint8_t *xok, int64_t n, int64_t p, double *out, uint8_t *ok);
+EXPORT int pqo_stochrsi(const double *x, const uint8_t *xok, int64_t n, int64_t timeperiod, int64_t fastk_period,
+                        int64_t fastd_period, int64_t fastd_matype, double *fastk, uint8_t *fastkok,
+                        double *fastd, uint8_t *fastdok) {
+    double *r = (double *)malloc(sizeof(double) * (size_t)(n + 1));
+    uint8_t *rok = (uint8_t *)malloc((size_t)(n + 1));
+    if (!r || !rok) { free(r); free(rok); return PQO_ERR_ALLOC; }
+    int rc = pqo_rsi(x, xok, n, timeperiod, r, rok);
+    if (!rc) rc = fastk_line(r, rok, r, rok, r, rok, n, fastk_period, fastk, fastkok);
+    if (!rc) rc = pqo_ma(fastk, fastkok, n, fastd_period, fastd_matype, fastd, fastdok);
+    free(r); free(rok);
+    return rc;
+}
+/* MACDEXT (momentum.py:83-88): macd = MA(real, fast, fastmatype) - MA(real, slow, slowmatype) (null where
+ * either is null), signal = MA(macd, signalperiod, signalmatype) (null-skipping, as every calc_ma),
+ * hist = macd - signal. */
+EXPORT int pqo_macdext(const double *x, const uint8_t *xok, int64_t n, int64_t fast, int64_t fastmatype,
+                       int64_t slow, int64_t slowmatype, int64_t signal, int64_t signalmatype,
+                       double *macd, uint8_t *macdok, double *sig, uint8_t *sigok, double *hist, uint8_t *histok) {
+    double *a = (double *)malloc(sizeof(double) * (size_t)(n + 1)), *b = (double *)malloc(sizeof(double) * (size_t)(n + 1));
+    uint8_t *aok = (uint8_t *)malloc((size_t)(n + 1)), *bok = (uint8_t *)malloc((size_t)(n + 1));
+    if (!a || !b || !aok || !bok) { free(a); free(b); free(aok); free(bok); return PQO_ERR_ALLOC; }
+    int rc = pqo_ma(x, xok, n, fast, fastmatype, a, aok);
+    if (!rc) rc = pqo_ma(x, xok, n, slow, slowmatype, b, bok);
+    if (!rc) {
+        for (int64_t i = 0; i < n; ++i) {
+            if (aok[i] && bok[i]) put_val(macd, macdok, i, a[i] - b[i]); else put_null(macd, macdok, i);
+        }
+        rc = pqo_ma(macd, macdok, n, signal, signalmatype, sig, sigok);
+    }
+    if (!rc) {
+        for (int64_t i = 0; i < n; ++i) {
+            if (macdok[i] && sigok[i]) put_val(hist, histok, i, macd[i] - sig[i]); else put_null(hist, histok, i);
+        }
+    }
+    free(a); free(b); free(aok); free(bok);
     return rc;
 }
 EXPORT int pqo_kdj(const double *h, const uint8_t *hok, const double *l, const uint8_t *lok,

@@ -107,6 +107,9 @@ def ema(x, p, ok=None): return _call("pqo_ema", [_col(x, ok)], [p], 1)
 def tema(x, p, ok=None): return _call("pqo_tema", [_col(x, ok)], [p], 1)
 def trima(x, p, ok=None): return _call("pqo_trima", [_col(x, ok)], [p], 1)
 def wma(x, p, ok=None): return _call("pqo_wma", [_col(x, ok)], [p], 1)
+def dema(x, p, ok=None): return _call("pqo_dema", [_col(x, ok)], [p], 1)
+def kama(x, p, ok=None): return _call("pqo_kama", [_col(x, ok)], [p], 1)
+def t3(x, p, vfactor=0.0, ok=None): return _call("pqo_t3", [_col(x, ok)], [p], 1, floats=[vfactor])
 def ma(x, p, matype=0, ok=None): return _call("pqo_ma", [_col(x, ok)], [p, matype], 1)
 def midpoint(x, p=14, ok=None): return _call("pqo_midpoint", [_col(x, ok)], [p], 1)
 def rsi(x, p=14, ok=None): return _call("pqo_rsi", [_col(x, ok)], [p], 1)
@@ -187,6 +190,14 @@ def stoch(h, l, c, fastk=5, slowk=3, slowk_matype=0, slowd=3, slowd_matype=0, ho
 
 def stochf(h, l, c, fastk=5, fastd=3, fastd_matype=0, hok=None, lok=None, cok=None):
     return _call("pqo_stochf", [_col(h, hok), _col(l, lok), _col(c, cok)], [fastk, fastd, fastd_matype], 2)
+
+
+def stochrsi(x, p=14, fastk=5, fastd=3, fastd_matype=0, ok=None):
+    return _call("pqo_stochrsi", [_col(x, ok)], [p, fastk, fastd, fastd_matype], 2)
+
+
+def macdext(x, fast=12, fastmatype=0, slow=26, slowmatype=0, signal=9, signalmatype=0, ok=None):
+    return _call("pqo_macdext", [_col(x, ok)], [fast, fastmatype, slow, slowmatype, signal, signalmatype], 3)
 
 
 def kdj(h, l, c, fastk=9, k=3, d=3):
