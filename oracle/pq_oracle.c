@@ -14,8 +14,8 @@
  * PARITY PINNED TO THE REFERENCE'S OWN OUTPUTS (round 2).  The reference ships no tests, golden vectors or
  * KATs for this path (its tests/__init__.py:1-4 is a scratch TA-Lib call) and cannot be compiled here (no Rust
  * toolchain; the snapshot has undefined symbols, e.g. calc_rma).  Its functions are, however, plain scalar
- * loops, so tests/golden/make_ref_golden.py EXECUTES the reference's source text (src/talib/*.rs through the
- * small Rust-subset interpreter in tests/golden/rustexec/, python/polars_quant/talib/*.py imported verbatim)
+ * loops, so tests/golden/make_ref_golden.py EXECUTES the reference's source text (the .rs files of src/talib through the
+ * small Rust-subset interpreter in tests/golden/rustexec/, the .py shims of python/polars_quant/talib imported verbatim)
  * and commits the outputs as tests/golden/talib_ref_golden.npz; tests/test_oracle_ref_golden.py holds every
  * function of this file to those vectors bit for bit (values, validity, and the inputs on which the reference
  * returns Err or panics).  Still defined here rather than by the reference: D1-D3 below (the reference's own

@@ -8,10 +8,12 @@
 // [symbol][pitch] f64 + LSB-first validity bitmaps; pack_kernel / unpack_kernel convert on the
 // device, chunk by chunk, on the way in and out.
 #include "../../include/pqb200.h"
+#include "../../include/pqb200_polars_plugin.h"   // the Arrow C Data Interface structs
 #include "suite_kernel.cuh"
 #include "candles.cuh"
 
 #include <algorithm>
+#include <atomic>
 #include <map>
 #include <cmath>
 #include <cstdarg>
@@ -107,6 +109,9 @@ struct pqb_engine {
     size_t host_pool_bytes = 0, host_pool_cap = 4ull << 30;
 };
 
+// page-locked host memory placed next to the engine's GPU (columns_host.inc: the calling thread runs on the GPU-local
+// CPUs while the driver allocates and pins the pages)
+static cudaError_t host_alloc_local(pqb_engine *e, void **out, size_t bytes);
 static cudaError_t host_take(pqb_engine *e, void **out, size_t bytes) {
     {
         std::lock_guard<std::mutex> lk(e->pool_mu);
@@ -118,7 +123,7 @@ static cudaError_t host_take(pqb_engine *e, void **out, size_t bytes) {
             return cudaSuccess;
         }
     }
-    cudaError_t ce = cudaMallocHost(out, bytes);
+    cudaError_t ce = host_alloc_local(e, out, bytes);
     if (ce == cudaSuccess) return ce;
     cudaGetLastError();
     {                                                   // out of pinned memory: give the pool back and try once more
@@ -127,7 +132,7 @@ static cudaError_t host_take(pqb_engine *e, void **out, size_t bytes) {
         e->host_pool.clear();
         e->host_pool_bytes = 0;
     }
-    return cudaMallocHost(out, bytes);
+    return host_alloc_local(e, out, bytes);
 }
 
 static void host_give(pqb_engine *e, void *ptr, size_t bytes) {
@@ -144,6 +149,9 @@ static void host_give(pqb_engine *e, void *ptr, size_t bytes) {
 }
 
 struct pqb_panel {
+    // the panel itself holds one reference, every outstanding Arrow export (pqb_panel_export_arrow) another: the
+    // pinned result planes an export aliases live until the last of them is released
+    std::atomic<int> refs{1};
     pqb_engine *e = nullptr;
     int64_t n_symbols = 0, n_bars = 0, pitch = 0, words_per_row = 0;
     int64_t n_blocks = 0, bars_padded = 0;   // tiled geometry
@@ -174,8 +182,11 @@ struct pqb_panel {
     std::vector<int32_t> h_lead[PQB_N_FIELDS];          // leading nulls seen by pqb_panel_set_column (-1: none given)
     std::vector<uint32_t> h_vin[PQB_N_FIELDS];          // row-major input validity bitmaps (empty: all valid)
     std::vector<uint8_t> h_flags;                       // per symbol: bit f = field f has an interior/trailing null
-    bool has_interior = false;
-    bool nulls_mode = false;                            // decided by prepare_nulls()
+    bool nulls_mode = false;                            // some symbol block needs the null-aware kernel (prepare_nulls)
+    std::vector<uint8_t> h_blk_null;                    // per symbol block: 1 = interior / trailing nulls or fields starting at different rows
+    int64_t n_null_blocks = 0;
+    std::vector<int> h_blist;                           // [2][n_blocks]: plain blocks, then null blocks, of the ranges launched so far
+    int *d_blist = nullptr;
     uint32_t *d_vin[PQB_N_FIELDS] = {};                 // row-major bitmaps on the device
     uint32_t *d_vmask = nullptr;                        // tiled [block][bar][4]
     uint32_t *d_ovm[PQB_N_OUTPUTS] = {};                // tiled [block][bar] per output
@@ -345,6 +356,7 @@ extern "C" int pqb_panel_create(pqb_engine *e, int64_t n_symbols, int64_t n_bars
     p->h_start_explicit.assign((size_t)n_symbols, 0);
     for (auto &v : p->h_lead) v.assign((size_t)n_symbols, -1);
     p->h_flags.assign((size_t)n_symbols, 0);
+    p->h_blk_null.assign((size_t)p->n_blocks, 0);
     if ((ce = cudaStreamSynchronize(e->stream)) != cudaSuccess) return bail(ce, "sync");
     *out = p;
     return PQB_OK;
@@ -352,6 +364,7 @@ extern "C" int pqb_panel_create(pqb_engine *e, int64_t n_symbols, int64_t n_bars
 
 extern "C" void pqb_panel_destroy(pqb_panel *p) {
     if (!p) return;
+    if (p->refs.fetch_sub(1) > 1) return;            // exports still alias the result planes: the last release frees
     if (p->e) cudaSetDevice(p->e->device);
     for (auto &q : p->d_in) if (q) cudaFree(q);
     for (auto &q : p->d_out) if (q) cudaFree(q);
@@ -363,6 +376,7 @@ extern "C" void pqb_panel_destroy(pqb_panel *p) {
     for (auto &q : p->d_ovm) if (q) cudaFree(q);
     if (p->d_vmask) cudaFree(p->d_vmask);
     if (p->d_flags) cudaFree(p->d_flags);
+    if (p->d_blist) cudaFree(p->d_blist);
     if (p->d_sig) cudaFree(p->d_sig);
     if (p->d_info) cudaFree(p->d_info);
     if (p->d_info_valid) cudaFree(p->d_info_valid);
@@ -407,6 +421,10 @@ extern "C" const uint8_t *pqb_panel_device_validity(const pqb_panel *p, int k) {
 }
 
 static inline bool bit_at(const uint8_t *bm, int64_t i) { return (bm[i >> 3] >> (i & 7)) & 1; }
+// (columns_host.inc)
+static void ensure_vin(pqb_panel *p, int field);
+static int stage_column(pqb_panel *p, int64_t symbol, int field, const void *values, char fmt, const uint8_t *validity,
+                        int64_t offset, int64_t len);
 
 extern "C" int pqb_panel_set_column(pqb_panel *p, int64_t symbol, int field, const double *values,
                                     const uint8_t *validity, int64_t offset, int64_t len) {
@@ -416,38 +434,8 @@ extern "C" int pqb_panel_set_column(pqb_panel *p, int64_t symbol, int field, con
         return fail(PQB_ERR_INVALID, "pqb_panel_set_column: bad symbol/field");
     if (len != p->n_bars || offset < 0)
         return fail(PQB_ERR_INVALID, "pqb_panel_set_column: len %lld != n_bars %lld", (long long)len, (long long)p->n_bars);
-    int64_t lead = 0;
-    bool interior = false;
-    if (validity) {
-        while (lead < len && !bit_at(validity, offset + lead)) ++lead;
-        for (int64_t i = lead; i < len; ++i)
-            if (!bit_at(validity, offset + i)) { interior = true; break; }
-    }
-    double *dst = p->h_in[field] + (size_t)symbol * p->pitch;
-    memcpy(dst, values + offset, (size_t)len * sizeof(double));
-    for (int64_t i = len; i < p->pitch; ++i) dst[i] = 0.0;
-    // validity bitmap of this column (kept for the null-aware mode); null slots get a benign value so
-    // that they never drive a division through its slow path
-    auto &vin = p->h_vin[field];
-    if (validity || !vin.empty()) {
-        if (vin.empty()) vin.assign((size_t)p->n_symbols * p->words_per_row, 0xffffffffu);
-        uint32_t *row = vin.data() + (size_t)symbol * p->words_per_row;
-        for (int64_t w = 0; w < p->words_per_row; ++w) {
-            uint32_t word = 0;
-            for (int j = 0; j < 32; ++j) {
-                const int64_t i = w * 32 + j;
-                if (i < len && (!validity || bit_at(validity, offset + i))) word |= 1u << j;
-            }
-            row[w] = word;
-        }
-        if (validity)
-            for (int64_t i = 0; i < len; ++i)
-                if (!bit_at(validity, offset + i)) dst[i] = 1.0;
-    }
-    p->h_lead[field][(size_t)symbol] = validity ? (int32_t)lead : 0;
-    if (interior) { p->has_interior = true; p->h_flags[(size_t)symbol] |= (uint8_t)(1u << field); }
-    else p->h_flags[(size_t)symbol] &= (uint8_t)~(1u << field);
-    return PQB_OK;
+    if (validity) ensure_vin(p, field);
+    return stage_column(p, symbol, field, values, 'g', validity, offset, len);
 }
 
 extern "C" int pqb_panel_set_starts(pqb_panel *p, const int32_t *starts) {
@@ -459,50 +447,64 @@ extern "C" int pqb_panel_set_starts(pqb_panel *p, const int32_t *starts) {
     return PQB_OK;
 }
 
-// Decides between the plain mode (every symbol valid on [start, n_bars), all fields alike) and the
-// null-aware mode (per-bar validity words), and ships starts / masks / flags to the device.
-static int prepare_nulls(pqb_panel *p, cudaStream_t st) {
-    bool nulls = p->has_interior;
-    for (size_t s = 0; s < (size_t)p->n_symbols && !nulls; ++s) {
-        int32_t lead = -2;
-        for (int f = 0; f < PQB_N_FIELDS; ++f) {
-            if (!p->d_in[f] || p->h_lead[f][s] < 0) continue;
-            if (lead == -2) lead = p->h_lead[f][s];
-            else if (lead != p->h_lead[f][s]) nulls = true;      // fields of one symbol start at different rows
+// Per symbol block of the range [s0, s0 + ns) (s0 a multiple of 32): plain (every symbol valid on [start, n_bars), all
+// fields alike -> the plain kernels, leading nulls folded into `start`) or null-aware (some symbol of the block has an
+// interior / trailing null, or fields starting at different rows -> per-bar validity words, the null-aware kernel).
+// The choice is per BLOCK (launch_suite makes one launch per kind over block lists), derived from what the columns
+// currently hold -- nothing sticky: overwriting a column with a null-free one returns its block to the plain kernel.
+// Ships starts / masks / flags of the range to the device on stream `st`.
+static int prepare_nulls(pqb_panel *p, cudaStream_t st, int64_t s0 = 0, int64_t ns = -1) {
+    if (ns < 0) ns = p->n_symbols - s0;
+    const int64_t b0 = s0 / SYM, b1 = (s0 + ns + SYM - 1) / SYM;
+    bool any_null = false;
+    for (int64_t b = b0; b < b1; ++b) {
+        bool nulls = false;
+        const size_t lo = (size_t)b * SYM, hi = (size_t)std::min<int64_t>((b + 1) * SYM, p->n_symbols);
+        for (size_t s = lo; s < hi && !nulls; ++s) {
+            if (p->h_flags[s]) { nulls = true; break; }
+            int32_t lead = -2;
+            for (int f = 0; f < PQB_N_FIELDS; ++f) {
+                if (!p->d_in[f] || p->h_lead[f][s] < 0) continue;
+                if (lead == -2) lead = p->h_lead[f][s];
+                else if (lead != p->h_lead[f][s]) nulls = true;      // fields of one symbol start at different rows
+            }
+        }
+        p->n_null_blocks += (int64_t)nulls - (int64_t)p->h_blk_null[(size_t)b];
+        p->h_blk_null[(size_t)b] = nulls ? 1 : 0;
+        any_null |= nulls;
+        for (size_t s = lo; s < hi; ++s) {
+            int32_t a = p->h_start_explicit[s];
+            if (!nulls)
+                for (int f = 0; f < PQB_N_FIELDS; ++f)
+                    if (p->d_in[f]) a = std::max(a, p->h_lead[f][s]);
+            p->h_start[s] = a;
+            if (a) p->starts_nonzero = true;                         // (sticky within a panel's life: only costs a pointer)
         }
     }
-    p->nulls_mode = nulls;
-    p->starts_nonzero = false;
-    for (size_t s = 0; s < (size_t)p->n_symbols; ++s) {
-        int32_t a = p->h_start_explicit[s];
-        if (!nulls)
-            for (int f = 0; f < PQB_N_FIELDS; ++f)
-                if (p->d_in[f]) a = std::max(a, p->h_lead[f][s]);
-        p->h_start[s] = a;
-        if (a) p->starts_nonzero = true;
-    }
-    CU(cudaMemcpyAsync(p->d_start, p->h_start.data(), (size_t)p->n_symbols * sizeof(int), cudaMemcpyHostToDevice, st));
-    if (!nulls) return PQB_OK;
+    p->nulls_mode = p->n_null_blocks > 0;
+    CU(cudaMemcpyAsync(p->d_start + s0, p->h_start.data() + s0, (size_t)ns * sizeof(int), cudaMemcpyHostToDevice, st));
+    if (!any_null) return PQB_OK;
     const size_t bplane = (size_t)p->n_symbols * p->words_per_row * sizeof(uint32_t);
     const size_t mwords = (size_t)p->n_blocks * p->bars_padded;
     if (!p->d_vmask) CU(cudaMalloc(&p->d_vmask, mwords * N_IN * sizeof(uint32_t)));
-    if (!p->d_flags) CU(cudaMalloc(&p->d_flags, (size_t)p->n_blocks * SYM));
-    CU(cudaMemsetAsync(p->d_flags, 0, (size_t)p->n_blocks * SYM, st));
-    CU(cudaMemcpyAsync(p->d_flags, p->h_flags.data(), (size_t)p->n_symbols, cudaMemcpyHostToDevice, st));
+    if (!p->d_flags) { CU(cudaMalloc(&p->d_flags, (size_t)p->n_blocks * SYM)); CU(cudaMemsetAsync(p->d_flags, 0, (size_t)p->n_blocks * SYM, st)); }
+    CU(cudaMemcpyAsync(p->d_flags + s0, p->h_flags.data() + s0, (size_t)ns, cudaMemcpyHostToDevice, st));
     MaskArgs V{};
+    const size_t roff = (size_t)s0 * p->words_per_row, rbytes = (size_t)ns * p->words_per_row * sizeof(uint32_t);
     for (int f = 0; f < PQB_N_FIELDS; ++f) {
         if (p->h_vin[f].empty()) continue;
         if (!p->d_vin[f]) CU(cudaMalloc(&p->d_vin[f], bplane));
-        CU(cudaMemcpyAsync(p->d_vin[f], p->h_vin[f].data(), bplane, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(p->d_vin[f] + roff, p->h_vin[f].data() + roff, rbytes, cudaMemcpyHostToDevice, st));
         V.rm[f] = p->d_vin[f];
     }
     for (int k = 0; k < PQB_N_OUTPUTS; ++k)
         if (p->d_out[k] && !p->d_ovm[k]) CU(cudaMalloc(&p->d_ovm[k], mwords * sizeof(uint32_t)));
     V.tiled_out = p->d_vmask;
-    V.start = p->starts_nonzero ? p->d_start : nullptr;
+    V.start = p->d_start;
     V.n_symbols = (int)p->n_symbols; V.n_bars = (int)p->n_bars; V.bars_padded = (int)p->bars_padded;
     V.words_per_row = (int)p->words_per_row; V.n_blocks = (int)p->n_blocks;
-    dim3 grid((unsigned)((p->bars_padded + 31) / 32), (unsigned)p->n_blocks);
+    V.block0 = (int)b0; V.blist = nullptr;
+    dim3 grid((unsigned)((p->bars_padded + 31) / 32), (unsigned)(b1 - b0));
     pack_mask_kernel<<<grid, 32, 0, st>>>(V);
     CU(cudaGetLastError());
     return PQB_OK;
@@ -713,18 +715,18 @@ static int build_args(const pqb_panel *p, const pqb_suite_params *sp, Built *out
     if ((ind & (PQB_IND_AD | PQB_IND_ADOSC | PQB_IND_MFI)) && (rc = need_fields(C | H | L | V, "ad / adosc / mfi"))) return rc;
     if ((ind & (PQB_IND_MIDPOINT | PQB_IND_MOM | PQB_IND_ROC | PQB_IND_CMO)) && (rc = need_fields(C, "close-based indicators"))) return rc;
     if ((ind & PQB_IND_CCI) && (rc = need_fields(C | H | L, "cci"))) return rc;
-    if ((ind & PQB_IND_EXTRAS) && p->nulls_mode)
-        return fail(PQB_ERR_UNSUPPORTED, "midpoint / adosc / mom / roc / cmo / mfi / cci are not built for panels with "
-                                         "interior nulls yet (momentum.rs functions fail on such input in the reference)");
 
     for (int f = 0; f < PQB_N_FIELDS; ++f) A.in[f] = p->d_in[f];
     for (int k = 0; k < PQB_N_OUTPUTS; ++k) { A.out[k] = nullptr; out->lead[k] = NEVER; }
     A.don_fold = 0; A.don_p = 1;
-    A.start = (p->starts_nonzero && !p->nulls_mode) ? p->d_start : nullptr;
-    A.vmask = p->nulls_mode ? p->d_vmask : nullptr;
-    A.symflags = p->nulls_mode ? p->d_flags : nullptr;
-    // validity words: every output in the null-aware mode; the optional groups always (roc / cci decide per bar)
-    for (int k = 0; k < PQB_N_OUTPUTS; ++k) A.ovm[k] = (p->nulls_mode || k >= PQB_N_SUITE_OUTPUTS) ? p->d_ovm[k] : nullptr;
+    // the arguments of the PLAIN kernels; launch_suite derives the null-aware variant (null_variant) for the symbol
+    // blocks that need it
+    A.start = p->starts_nonzero ? p->d_start : nullptr;
+    A.vmask = nullptr;
+    A.symflags = nullptr;
+    A.blist = nullptr;
+    // validity words: the optional groups always (roc / cci decide per bar); every output in the null-aware variant
+    for (int k = 0; k < PQB_N_OUTPUTS; ++k) A.ovm[k] = (k >= PQB_N_SUITE_OUTPUTS) ? p->d_ovm[k] : nullptr;
     A.n_symbols = (int)p->n_symbols;
     A.n_bars = n_bars;
     A.n_blocks = (int)p->n_blocks;
@@ -1009,6 +1011,16 @@ static void deal_base_slots(SuiteArgs &A) {
     A.n_roles = n;
 }
 
+// the null-aware variant of a launch's arguments: per-bar validity words in, per-bar validity words out, starts folded
+// into the masks
+static SuiteArgs null_variant(const pqb_panel *p, SuiteArgs a) {
+    a.start = nullptr;
+    a.vmask = p->d_vmask;
+    a.symflags = p->d_flags;
+    for (int k = 0; k < PQB_N_OUTPUTS; ++k) a.ovm[k] = p->d_ovm[k];
+    return a;
+}
+
 // Launches the suite over symbol blocks [b0, b0+nb) (+ NaN fills + validity bitmaps of those symbols).
 static int launch_suite(pqb_panel *p, const Built &full, int64_t b0, int64_t nb, cudaEvent_t ev_after_fused,
                         int *launches) {
@@ -1024,8 +1036,11 @@ static int launch_suite(pqb_panel *p, const Built &full, int64_t b0, int64_t nb,
         }
     }
     // one launch of the fused kernel for the groups of `a` (variant selection + tail spreading)
-    auto launch_one = [&](SuiteArgs a) -> int {
-        a.block0 = (int)b0;
+    // nl blocks: the range [b0, b0 + nb) itself (list == nullptr) or the device list `list` of nl absolute block ids
+    auto launch_one = [&](SuiteArgs a, const int *list, int64_t nl) -> int {
+        const int64_t nb = nl;                                // (shadows the range length: variant selection goes by this launch)
+        a.block0 = list ? 0 : (int)b0;
+        a.blist = list;
         derive_roles(a);
 #ifdef PQB_DEBUG_CLOCKS      // tuning build: per-role busy cycles of the first block (costs ~18% on config 4)
         if (!g_dbg) CU(cudaMalloc(&g_dbg, N_ROLES * sizeof(unsigned long long)));
@@ -1084,14 +1099,43 @@ static int launch_suite(pqb_panel *p, const Built &full, int64_t b0, int64_t nb,
         // kernel: 50,000 x 5,040 suite + MOM 23.2 ms in one general launch).  Null-aware mode has one kernel for everything.
         const unsigned gb = full.a.gmask & (unsigned)G_ALL, go = full.a.gmask & ~(unsigned)G_ALL;
         int rc;
-        if (gb && go && !full.a.vmask && split_launch_enabled()) {
-            SuiteArgs ab = full.a, ao = full.a;
-            ab.gmask = gb;
-            ao.gmask = go;
-            if ((rc = layout_rings(ab, p)) || (rc = layout_rings(ao, p))) return rc;      // (subsets of a layout that fits)
-            if ((rc = launch_one(ab))) return rc;
-            if ((rc = launch_one(ao))) return rc;
-        } else if ((rc = launch_one(full.a))) return rc;
+        // which blocks of the range need the null-aware kernel
+        int64_t n_null = 0;
+        if (p->nulls_mode)
+            for (int64_t b = b0; b < b0 + nb; ++b) n_null += p->h_blk_null[(size_t)b];
+        if (n_null && go)
+            return fail(PQB_ERR_UNSUPPORTED, "midpoint / adosc / mom / roc / cmo / mfi / cci / ... are not built for panels with "
+                                             "interior nulls yet (momentum.rs functions fail on such input in the reference)");
+        const int *plain_list = nullptr, *null_list = nullptr;
+        if (n_null && n_null < nb) {
+            if (!p->d_blist) CU(cudaMalloc(&p->d_blist, (size_t)p->n_blocks * 2 * sizeof(int)));
+            if (p->h_blist.empty()) p->h_blist.assign((size_t)p->n_blocks * 2, 0);
+            int *hp = p->h_blist.data() + b0, *hn = p->h_blist.data() + p->n_blocks + b0;
+            int64_t np_ = 0, nn = 0;
+            for (int64_t b = b0; b < b0 + nb; ++b) {
+                if (p->h_blk_null[(size_t)b]) hn[nn++] = (int)b; else hp[np_++] = (int)b;
+            }
+            CU(cudaMemcpyAsync(p->d_blist + b0, hp, (size_t)np_ * sizeof(int), cudaMemcpyHostToDevice, e->stream));
+            CU(cudaMemcpyAsync(p->d_blist + p->n_blocks + b0, hn, (size_t)nn * sizeof(int), cudaMemcpyHostToDevice, e->stream));
+            plain_list = p->d_blist + b0;
+            null_list = p->d_blist + p->n_blocks + b0;
+        }
+        if (n_null < nb) {                                    // the plain blocks
+            const int64_t nl = nb - n_null;
+            if (gb && go && split_launch_enabled()) {
+                SuiteArgs ab = full.a, ao = full.a;
+                ab.gmask = gb;
+                ao.gmask = go;
+                if ((rc = layout_rings(ab, p)) || (rc = layout_rings(ao, p))) return rc;      // (subsets of a layout that fits)
+                if ((rc = launch_one(ab, plain_list, nl))) return rc;
+                if ((rc = launch_one(ao, plain_list, nl))) return rc;
+            } else if ((rc = launch_one(full.a, plain_list, nl))) return rc;
+        }
+        if (n_null) {                                         // the flagged blocks: one null-aware launch
+            SuiteArgs an = null_variant(p, full.a);
+            if (!an.smem_bytes && (rc = layout_rings(an, p))) return rc;
+            if ((rc = launch_one(an, null_list, n_null))) return rc;
+        }
     }
 #ifdef PQB_DEBUG_CLOCKS
     if (g_dbg && full.a.gmask) {
@@ -1105,54 +1149,43 @@ static int launch_suite(pqb_panel *p, const Built &full, int64_t b0, int64_t nb,
 #endif
     if (ev_after_fused) CU(cudaEventRecord(ev_after_fused, e->stream));
     const int64_t s0 = b0 * SYM, ns = std::min<int64_t>(nb * SYM, p->n_symbols - s0);
-    if (p->nulls_mode) {
-        // the kernel wrote per-bar validity words; turn them into the Arrow bitmaps of these symbols
+    int64_t n_null = 0;
+    if (p->nulls_mode)
+        for (int64_t b = b0; b < b0 + nb; ++b) n_null += p->h_blk_null[(size_t)b];
+    // validity words written by a kernel -> Arrow bitmaps: outputs [k0, N) of the blocks `list` (or of the whole range)
+    auto unpack_masks = [&](int k0, const int *list, int64_t nl, bool clear_unstored) -> int {
         MaskArgs M{};
         int n = 0;
-        for (int k = 0; k < PQB_N_OUTPUTS; ++k) {
+        for (int k = k0; k < PQB_N_OUTPUTS; ++k) {
             if (!(full.a.out[k] && p->d_bits[k])) continue;
             if (stored >> k & 1) {
-                M.tiled_in[n] = p->d_ovm[k] + (size_t)b0 * p->bars_padded;
-                M.rm_out[n] = p->d_bits[k] + (size_t)s0 * p->words_per_row;
+                M.tiled_in[n] = p->d_ovm[k];
+                M.rm_out[n] = p->d_bits[k];
                 ++n;
-            } else {
+            } else if (clear_unstored) {
                 CU(cudaMemsetAsync(p->d_bits[k] + (size_t)s0 * p->words_per_row, 0,
                                    (size_t)ns * p->words_per_row * sizeof(uint32_t), e->stream));
             }
         }
-        M.n_planes = n; M.n_symbols = (int)ns; M.n_bars = (int)p->n_bars; M.bars_padded = (int)p->bars_padded;
-        M.words_per_row = (int)p->words_per_row; M.n_blocks = (int)nb;
-        if (n) {
-            dim3 grid((unsigned)p->words_per_row, (unsigned)nb);
-            unpack_mask_kernel<<<grid, 32, 0, e->stream>>>(M);
-            CU(cudaGetLastError());
-            ++n_launch;
-        }
-        if (launches) *launches = n_launch;
+        if (!n || !nl) return PQB_OK;
+        M.n_planes = n; M.n_symbols = (int)p->n_symbols; M.n_bars = (int)p->n_bars; M.bars_padded = (int)p->bars_padded;
+        M.words_per_row = (int)p->words_per_row; M.n_blocks = (int)nl;
+        M.block0 = (int)b0; M.blist = list;
+        dim3 grid((unsigned)p->words_per_row, (unsigned)nl);
+        unpack_mask_kernel<<<grid, 32, 0, e->stream>>>(M);
+        CU(cudaGetLastError());
+        ++n_launch;
         return PQB_OK;
+    };
+    if (n_null == nb) {
+        // every block of the range ran the null-aware kernel: all validity comes from its per-bar words
+        int rc = unpack_masks(0, nullptr, nb, true);
+        if (launches) *launches = n_launch;
+        return rc;
     }
     {   // optional groups: validity words written by the kernel (or all-null for a period-0 column)
-        MaskArgs M{};
-        int n = 0;
-        for (int k = PQB_N_SUITE_OUTPUTS; k < PQB_N_OUTPUTS; ++k) {
-            if (!(full.a.out[k] && p->d_bits[k])) continue;
-            if (stored >> k & 1) {
-                M.tiled_in[n] = p->d_ovm[k] + (size_t)b0 * p->bars_padded;
-                M.rm_out[n] = p->d_bits[k] + (size_t)s0 * p->words_per_row;
-                ++n;
-            } else {
-                CU(cudaMemsetAsync(p->d_bits[k] + (size_t)s0 * p->words_per_row, 0,
-                                   (size_t)ns * p->words_per_row * sizeof(uint32_t), e->stream));
-            }
-        }
-        if (n) {
-            M.n_planes = n; M.n_symbols = (int)ns; M.n_bars = (int)p->n_bars; M.bars_padded = (int)p->bars_padded;
-            M.words_per_row = (int)p->words_per_row; M.n_blocks = (int)nb;
-            dim3 grid((unsigned)p->words_per_row, (unsigned)nb);
-            unpack_mask_kernel<<<grid, 32, 0, e->stream>>>(M);
-            CU(cudaGetLastError());
-            ++n_launch;
-        }
+        int rc = unpack_masks(PQB_N_SUITE_OUTPUTS, nullptr, nb, true);
+        if (rc) return rc;
     }
     ValidityArgs V{};
     bool any = false;
@@ -1171,6 +1204,11 @@ static int launch_suite(pqb_panel *p, const Built &full, int64_t b0, int64_t nb,
         validity_kernel<<<grid, 256, 0, e->stream>>>(V);
         CU(cudaGetLastError());
         ++n_launch;
+    }
+    if (n_null) {
+        // mixed range: the flagged blocks' bitmaps come from the null-aware kernel's words (overwriting the lead-based ones)
+        int rc = unpack_masks(0, p->d_blist + p->n_blocks + b0, n_null, false);
+        if (rc) return rc;
     }
     if (launches) *launches = n_launch;
     return PQB_OK;
@@ -1208,7 +1246,9 @@ extern "C" int pqb_suite_run(pqb_panel *p, const pqb_suite_params *sp) { return 
 //   d2h stream : outputs + bitmaps -> pinned staging
 // so both DMA directions overlap the kernels of neighbouring chunks.
 // ---------------------------------------------------------------------------------------
-extern "C" int pqb_suite_run_host(pqb_panel *p, const pqb_suite_params *sp, int64_t chunk_symbols) {
+struct IntakeGate;
+static void intake_wait(const IntakeGate *g, int64_t chunk);
+static int run_host_impl(pqb_panel *p, const pqb_suite_params *sp, int64_t chunk_symbols, const IntakeGate *gate) {
     if (!p || !sp) return fail(PQB_ERR_INVALID, "pqb_suite_run_host: NULL argument");
     if (!p->staging) return fail(PQB_ERR_INVALID, "pqb_suite_run_host: panel has no host staging");
     int rc = set_dev(p->e);
@@ -1224,13 +1264,17 @@ extern "C" int pqb_suite_run_host(pqb_panel *p, const pqb_suite_params *sp, int6
     std::vector<cudaEvent_t> up((size_t)n_chunks), done((size_t)n_chunks);
     for (auto &x : up) CU(cudaEventCreateWithFlags(&x, cudaEventDisableTiming));
     for (auto &x : done) CU(cudaEventCreateWithFlags(&x, cudaEventDisableTiming));
-    if ((rc = prepare_nulls(p, e->h2d))) return rc;
-    if ((rc = build_args(p, sp, &full))) return rc;      // (mode may have changed)
+    // null bookkeeping -> device: the whole panel up front, or (pipelined intake) chunk by chunk as the columns arrive
+    if (!gate && (rc = prepare_nulls(p, e->h2d))) return rc;
     int total_launches = 0;
     for (int64_t c = 0; c < n_chunks; ++c) {
         const int b = (int)(c & 1);
         const int64_t s0 = c * chunk_symbols, ns = std::min(chunk_symbols, p->n_symbols - s0);
         const size_t rows = (size_t)ns * p->pitch * sizeof(double);
+        if (gate) {
+            intake_wait(gate, c);
+            if ((rc = prepare_nulls(p, e->h2d, s0, ns))) return rc;
+        }
         // ---- H2D (buffer b is free once the pack of chunk c-2 has read it) ----
         if (c >= 2) CU(cudaStreamWaitEvent(e->h2d, p->ev_packed[b], 0));
         const double *rm_in[PQB_N_FIELDS];
@@ -1280,6 +1324,10 @@ extern "C" int pqb_suite_run_host(pqb_panel *p, const pqb_suite_params *sp, int6
     p->last_launches = total_launches;
     p->inputs_resident = true;
     return PQB_OK;
+}
+
+extern "C" int pqb_suite_run_host(pqb_panel *p, const pqb_suite_params *sp, int64_t chunk_symbols) {
+    return run_host_impl(p, sp, chunk_symbols, nullptr);
 }
 
 extern "C" int pqb_panel_last_launches(const pqb_panel *p) { return p ? p->last_launches : 0; }
@@ -1552,7 +1600,6 @@ static int run_single(pqb_engine *e, const pqb_col *const *cols, const int *fiel
     p->h_start[0] = 0;
     p->h_start_explicit[0] = 0;
     p->starts_nonzero = false;
-    p->has_interior = false;
     p->h_flags[0] = 0;
     for (int f = 0; f < PQB_N_FIELDS; ++f) { p->h_lead[f][0] = -1; p->h_vin[f].clear(); }
     for (int i = 0; i < n_cols; ++i)
@@ -1862,6 +1909,7 @@ extern "C" int pqb_multi_run_host(pqb_multi *m, const pqb_suite_params *params) 
     return PQB_OK;
 }
 
+#include "columns_host.inc"
 #include "candles_host.inc"
 #include "split_host.inc"
 #include "signals_host.inc"

@@ -42,7 +42,7 @@ def test_no_cpu_fallback_without_a_device(lib):
     import torch
     if torch.cuda.is_available():
         pytest.skip("a GPU is present")
-    assert lib.pqb_abi_version() == 4
+    assert lib.pqb_abi_version() == 5
     assert lib.pqb_device_count() == 0
     h = C.c_void_p()
     rc = lib.pqb_engine_create(0, C.byref(h))
@@ -84,3 +84,10 @@ def test_split_required_warmup_rules(lib):
     assert (1.0 - a) ** (e - 5000) < 1e-12                              # the seed error is forgotten below the tolerance
     assert w(indicators=N.IND["rsi"], rsi_period=14) >= 29 * 14
     assert (1.0 - 1.0 / 14) ** (29 * 14 - 14) < 1e-12
+    # groups added after the time-split code must be named explicitly to be splittable: running sums
+    # (ULTOSC, CMO, MFI, CCI) are refused, the Wilder / EMA cascades ask for their own warm-up
+    assert w(indicators=N.IND_EXTRA["ultosc"]) == -1 and w(indicators=N.IND_EXTRA["cmo"]) == -1
+    assert w(indicators=N.IND_EXTRA["trix"], trix_period=30) >= 3 * (30 + 14 * 31)
+    assert w(indicators=N.IND_EXTRA["dm"], dm_period=14) >= 2 * 29 * 14
+    assert w(indicators=N.IND_EXTRA["aroon"], aroon_period=40) == 64
+    assert w(indicators=1 << 27) == -1                                  # an unknown group bit is never splittable
