@@ -5,14 +5,16 @@
 
 A "step" is one pass of the fused 15-indicator / 21-output suite over one synthetic random-walk
 OHLCV panel already resident in HBM.  N > 1 is launched by torchrun, one process per GPU; symbols
-are independent so every rank runs its own panel of the full workload shape (weak scaling, no
-collective on the data path); torch.distributed (NCCL) is used only for the barrier and the
-max-over-ranks of the device-timed duration.
+are independent, so the workload's 50,000 symbols are SHARDED over the ranks in contiguous ranges of
+whole 32-symbol blocks (strong scaling -- BASELINE config 4; `--scaling weak` runs the full shape on
+every rank), with no collective on the data path; torch.distributed (NCCL) is used only for the
+barrier and the max-over-ranks of the timed durations.
 
 Keys beyond the base contract:
   roofline      dominant kernel (suite_fused_kernel) vs the measured HBM copy peak
   cpu_baseline  the C oracle (a port of the reference's Rust loops) on this box's host cores
-  e2e           same metric through the C ABI with HOST (pinned) buffers: H2D + kernels + D2H
+  e2e           same metric through the public column API: caller-owned column buffers in (pageable host memory),
+                Arrow result columns out, every host copy and both PCIe directions inside the timed region
 `--impl reference` times the reference's own CPU path -- the C oracle port, since the Rust crate
 cannot be built in this image -- on all host cores, same config/metric/unit.
 """
@@ -177,13 +179,59 @@ def run_reference(args, shape, rank, world):
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "higher_is_better": True, "scaling": getattr(args, "scaling", "strong"), "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": desc, "symbols": S, "bars": N, "sample": sample},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": used, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+def traffic_record(S, N):
+    """ncu DRAM bytes of the dominant kernel for this shape, with the commit it was captured at (profiles/traffic.json,
+    written by scripts/ncu_traffic.sh from an `ncu --set full` capture; never measured under the timer)."""
+    tp = ROOT / "profiles" / "traffic.json"
+    if not tp.exists():
+        return None, None
+    try:
+        tj = json.loads(tp.read_text())
+        for rec in (tj if isinstance(tj, list) else [tj]):
+            if rec.get("symbols") == S and rec.get("bars") == N:
+                return rec.get("dram_bytes_per_launch"), {k: rec.get(k) for k in ("captured_at_commit", "kernel", "source") if rec.get(k)}
+    except Exception:
+        pass
+    return None, None
+
+
+def bench_c3(pq, NV, engine, peak, iters=5):
+    """BASELINE config 3: 500 x 1,000,000, EMA(12, 26, 200, 5000) + MACD(12, 26, 9): 1 plane in, 7 out = 64 B per
+    symbol-bar."""
+    from polars_quant_b200 import longrows
+    S, NB = 500, 1_000_000
+    lp = longrows.LongPanel(S, NB, engine=engine, ema_periods=(12, 26, 200, 5000), macd=(12, 26, 9), host_staging=False)
+    lp.fill_synthetic(seed=3, sigma=0.0005)
+    ms, launches = lp.time_device(warmup=2, iters=iters)
+    lp.close()
+    g = 64 * S * NB / (ms * 1e-3) / 1e9
+    return {"workload": "BASELINE config 3: 500 symbols x 1,000,000 minute bars, EMA(12,26,200,5000) + MACD(12,26,9) in one pass",
+            "kernel": "ema_scan_kernel", "launches": launches, "kernel_ms": ms, "value": S * NB / (ms * 1e-3), "unit": UNIT,
+            "algorithmic_bytes_per_symbol_bar": 64, "achieved_gbs": g, "frac": g / peak}
+
+
+def bench_c5(pq, NV, engine, peak, iters=5):
+    """BASELINE config 5: 10,000 x 5,040, KDJ(k) for k in 5/9/14/60/250 + WILLR / MIDPRICE / Donchian(p) for p in
+    5/20/55/250 + ATR(14): 3 planes in, 28 out = 248 B per symbol-bar."""
+    from polars_quant_b200 import windows
+    S, NB = 10_000, 5_040
+    wp = windows.WindowPanel(S, NB, engine=engine, kdj=(5, 9, 14, 60, 250), ext=(5, 20, 55, 250), atr=14, host_staging=False)
+    wp.fill_synthetic(seed=55, sigma=0.02)
+    ms, launches = wp.time_device(warmup=2, iters=iters)
+    wp.close()
+    g = 248 * S * NB / (ms * 1e-3) / 1e9
+    return {"workload": "BASELINE config 5: 10,000 x 5,040, KDJ(5,9,14,60,250) + WILLR/MIDPRICE/Donchian(5,20,55,250) + ATR(14)",
+            "kernel": "window_suite_kernel", "launches": launches, "kernel_ms": ms, "value": S * NB / (ms * 1e-3), "unit": UNIT,
+            "algorithmic_bytes_per_symbol_bar": 248, "achieved_gbs": g, "frac": g / peak}
 
 
 def main():
@@ -193,11 +241,15 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
-    ap.add_argument("--symbols", type=int, default=0, help="override symbols per GPU")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="strong (default): the workload's symbols are sharded over the GPUs (BASELINE config 4: '50,000 x 5,040 "
+                         "symbol-sharded at 1/2/4/8'); weak: every GPU runs the whole workload shape")
+    ap.add_argument("--symbols", type=int, default=0, help="override the workload's symbol count")
     ap.add_argument("--bars", type=int, default=0)
-    ap.add_argument("--no-extra", action="store_true", help="skip the kernel-only lines of the other shapes (config 2, candles)")
-    ap.add_argument("--e2e-symbols", type=int, default=8192, help="symbols of the workload pushed through the host path")
+    ap.add_argument("--no-extra", action="store_true", help="skip the kernel-only lines of the other shapes (configs 2, 3, 5, candles)")
+    ap.add_argument("--e2e-symbols", type=int, default=0, help="symbols per GPU pushed through the column API (0: the GPU's whole share)")
     ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--threads", type=int, default=0, help="host threads of the column intake per GPU (0: cores / GPUs, at most 16)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
@@ -207,14 +259,14 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    S, N, desc = WORKLOADS[args.workload]
+    S_total, N, desc = WORKLOADS[args.workload]
     if args.symbols:
-        S = args.symbols
+        S_total = args.symbols
     if args.bars:
         N = args.bars
 
     if args.impl == "reference":
-        run_reference(args, (S, N, desc), rank, world)
+        run_reference(args, (S_total, N, desc), rank, world)
         return
 
     dist = None
@@ -241,10 +293,28 @@ def main():
 
     import polars_quant_b200 as pq
     from polars_quant_b200 import _native as NV
+    from polars_quant_b200.shard import symbol_range
 
     def barrier():
         if dist is not None:
             dist.barrier()
+
+    def max_over_ranks(*vals):
+        if dist is None:
+            return vals
+        import torch
+        t = torch.tensor(list(vals), dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return tuple(float(x) for x in t)
+
+    # this GPU's share of the panel: contiguous whole 32-symbol blocks, or the whole shape (weak)
+    if args.scaling == "strong":
+        lo, hi = symbol_range(S_total, world, rank)
+        S = hi - lo
+        units = S_total * N
+    else:
+        lo, S = 0, S_total
+        units = S_total * N * world
 
     engine = pq.get_engine(local_rank)
     params = NV.default_params()
@@ -256,69 +326,117 @@ def main():
     with ClockSampler(local_rank) as clocks:
         ms_total, ms_fused, launches = panel.time_device(params, warmup=args.warmup, iters=args.steps)
     barrier()
-    if dist is not None:
-        import torch
-        t = torch.tensor([ms_total, ms_fused], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total, ms_fused = float(t[0]), float(t[1])
-    units = S * N * world
+    ms_total, ms_fused = max_over_ranks(ms_total, ms_fused)
     value = units * args.steps / (ms_total * 1e-3)
     peak, peak_src = measured_peak()
     fused_ms_avg = ms_fused / args.steps
+    # roofline of THIS rank's launch (the slowest rank's duration): algorithmic bytes of its own share
     achieved = ALGO_BYTES_PER_SYMBOL_BAR * S * N / (fused_ms_avg * 1e-3) / 1e9
+    panel.close()
 
-    # ---- end to end through the C ABI with host buffers ----
-    e2e = None
+    # ---- end to end through the public column API ------------------------------------------------------------------
+    # One step = what a caller of the panel API does with a wide table: caller-owned f64 column buffers (ordinary
+    # pageable host memory, one per {symbol}_{field}) -> pqb_suite_run_columns (thread-pool intake into pinned staging,
+    # pipelined with H2D || pack + fused suite + unpack || D2H) -> pqb_panel_export_arrow (all result columns as one
+    # Arrow struct array over the pinned result planes) -> release.  Timed by the host clock around the calls (they
+    # return after the last D2H has landed), max over ranks.
+    e2e, cpu = None, None
     e2e_launches = 0
     if not args.no_e2e:
-        Se = min(S, args.e2e_symbols)
-        hp = pq.Panel(Se, N, engine=engine, host_staging=True)
+        import ctypes as C
+        Se = min(S, args.e2e_symbols) if args.e2e_symbols else S
+        threads = args.threads or max(1, min(16, (os.cpu_count() or 1) // max(world, 1)))
+        hp = None
+        while hp is None:
+            try:
+                hp = pq.Panel(Se, N, engine=engine, host_staging=True)
+            except NV.PqbError as ex:                      # not enough page-lockable memory on this box: halve the slab
+                if Se <= 1024:
+                    raise
+                sys.stderr.write("[bench] pinned staging for %d symbols failed (%s); halving\n" % (Se, ex))
+                Se //= 2
         hp.fill_synthetic(seed=0xC0FFEE + 1_000_003 * rank, sigma=0.02, to_host=True)
+        # the caller's own column buffers: copies of the panel in pageable memory, one [Se, N] matrix per field whose
+        # rows are the {symbol}_{field} columns
+        mats = {f: np.array(hp.host_field(f)[:Se, :N]) for f in ("close", "high", "low", "volume")}
+        refs, _keep = pq.Panel.field_refs(**mats)
+        arr, sch = NV.ArrowArray(), NV.ArrowSchema()
+        rel_a = C.CFUNCTYPE(None, C.POINTER(NV.ArrowArray))
+        rel_s = C.CFUNCTYPE(None, C.POINTER(NV.ArrowSchema))
+
+        def step():
+            hp.run_columns(refs, params, threads=threads)
+            NV.check(NV.lib().pqb_panel_export_arrow(hp._h, 0, None, C.byref(arr), C.byref(sch)))
+            n_cols = arr.n_children
+            rel_a(arr.release)(C.pointer(arr))
+            rel_s(sch.release)(C.pointer(sch))
+            return n_cols
+
+        step()                                              # warm-up (also pins / touches everything once)
         barrier()
-        ms_host = hp.time_host(params, chunk_symbols=0, warmup=1, iters=args.e2e_steps)
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            n_cols_out = step()
+        dt = time.perf_counter() - t0
         barrier()
-        if dist is not None:
-            import torch
-            t = torch.tensor([ms_host], dtype=torch.float64, device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms_host = float(t[0])
+        (ms_host,) = max_over_ranks(dt * 1e3)
         pitch = hp.pitch
-        e2e = {"value": Se * N * world * args.e2e_steps / (ms_host * 1e-3), "unit": UNIT,
+        e2e_units = Se * N * world if args.scaling == "weak" or Se != S else units
+        e2e = {"value": e2e_units * args.e2e_steps / (ms_host * 1e-3), "unit": UNIT,
                "h2d_bytes_per_step": int(N_IN * Se * pitch * 8 + Se * 4),
                "d2h_bytes_per_step": int(N_OUT * Se * pitch * 8 + N_OUT * Se * hp.validity_pitch),
-               "symbols": Se, "bars": N, "ms_per_step": ms_host / args.e2e_steps,
-               "note": "row-major pinned host panel -> chunked H2D || pack + fused suite + unpack || D2H on 3 streams; PCIe-bound"}
+               "symbols_per_gpu": Se, "bars": N, "ms_per_step": ms_host / args.e2e_steps, "intake_threads_per_gpu": threads,
+               "input_columns_per_gpu": int(len(refs)), "output_columns_per_gpu": int(n_cols_out),
+               "timed": "host clock around pqb_suite_run_columns + pqb_panel_export_arrow, max over ranks",
+               "note": "caller-owned pageable column buffers -> thread-pool intake into pinned staging || chunked H2D || "
+                       "pack + fused suite + unpack || D2H -> one Arrow struct array over the pinned result planes; PCIe-bound"}
         e2e_launches = hp.last_launches() * args.e2e_steps
 
         # ---- CPU baseline on rank 0: the oracle port over a bounded sample of the same panel ----
-        cpu = None
         if rank == 0 and not args.no_cpu:
             cores = os.cpu_count() or 1
             ns = min(Se, max(64, 16 * cores))
-            c, h, l, v = (np.ascontiguousarray(hp.host_field(f)[:ns, :N]) for f in ("close", "high", "low", "volume"))
+            c, h, l, v = (np.ascontiguousarray(mats[f][:ns]) for f in ("close", "high", "low", "volume"))
             rate, used, reps = cpu_suite_rate(c, h, l, v, cores, args.cpu_seconds)
             cpu = {"value": rate, "unit": UNIT, "cores": used, "kind": "port",
                    "sample": f"{ns} symbols x {N} bars of the same synthetic panel, {reps} passes, C oracle (oracle/pq_oracle.c)"}
+        del refs, _keep, mats
         hp.close()
-    else:
-        cpu = None
 
     # ---- the other measured shapes of BASELINE.json / SURVEY.md 8f, kernel-only, reported beside the headline
-    #      (N=1 only; a few seconds): config 2 on the same suite kernel, and the fused candle kernel ----
+    #      (N=1 only; a few seconds each): configs 2, 3, 5, the candle kernel and the access-mix ceiling ----
     other = None
     if world == 1 and not args.no_extra:
         other = {}
-        try:
-            panel.close()
-            if (S, N) != WORKLOADS["c2"][:2]:
-                S2, N2, d2 = WORKLOADS["c2"]
-                p2 = pq.Panel(S2, N2, engine=engine, host_staging=False)
-                p2.fill_synthetic(seed=0xC0FFEE, sigma=0.02)
-                _, f2, _ = p2.time_device(params, warmup=3, iters=20)
-                p2.close()
-                g2 = ALGO_BYTES_PER_SYMBOL_BAR * S2 * N2 / (f2 / 20 * 1e-3) / 1e9
-                other["c2"] = {"workload": d2, "kernel": "suite_fused_kernel<true,false>", "kernel_ms": f2 / 20,
-                               "value": S2 * N2 / (f2 / 20 * 1e-3), "unit": UNIT, "achieved_gbs": g2, "frac": g2 / peak}
+
+        def extra(name, fn):
+            try:
+                other[name] = fn()
+            except Exception as ex:      # never lose the headline line to an extra
+                other[name] = {"error": repr(ex)}
+
+        def c2():
+            S2, N2, d2 = WORKLOADS["c2"]
+            p2 = pq.Panel(S2, N2, engine=engine, host_staging=False)
+            p2.fill_synthetic(seed=0xC0FFEE, sigma=0.02)
+            _, f2, _ = p2.time_device(params, warmup=3, iters=20)
+            p2.close()
+            g2 = ALGO_BYTES_PER_SYMBOL_BAR * S2 * N2 / (f2 / 20 * 1e-3) / 1e9
+            return {"workload": d2, "kernel": "suite_fused_kernel<true,false,false,true>", "kernel_ms": f2 / 20,
+                    "value": S2 * N2 / (f2 / 20 * 1e-3), "unit": UNIT, "achieved_gbs": g2, "frac": g2 / peak}
+
+        def shard8():
+            # the strong-scaled shape one GPU of eight runs (6,250 symbols): what SCALE's 8-GPU point is made of
+            S8 = symbol_range(WORKLOADS["c4"][0], 8, 0)[1]
+            p8 = pq.Panel(S8, WORKLOADS["c4"][1], engine=engine, host_staging=False)
+            p8.fill_synthetic(seed=0xC0FFEE, sigma=0.02)
+            _, f8, _ = p8.time_device(params, warmup=3, iters=20)
+            p8.close()
+            g8 = ALGO_BYTES_PER_SYMBOL_BAR * S8 * WORKLOADS["c4"][1] / (f8 / 20 * 1e-3) / 1e9
+            return {"workload": "one GPU's share of config 4 at 8 GPUs: %d x %d" % (S8, WORKLOADS["c4"][1]),
+                    "kernel_ms": f8 / 20, "value": S8 * WORKLOADS["c4"][1] / (f8 / 20 * 1e-3), "unit": UNIT, "achieved_gbs": g8, "frac": g8 / peak}
+
+        def candle():
             from polars_quant_b200 import candles
             Sc, Nc = 20_000, 5_040
             cp = candles.CandlePanel(Sc, Nc, engine=engine, host_staging=False)
@@ -326,45 +444,45 @@ def main():
             msc = cp.time_device(warmup=3, iters=10) / 10
             cp.close()
             gc = 316 * Sc * Nc / (msc * 1e-3) / 1e9
-            other["candles"] = {"workload": "SURVEY 8f.1: 61 cdl* patterns + 4 price transforms + bop, 20,000 x 5,040 random-walk OHLC",
-                                "kernel": "candle_kernel<true>", "kernel_ms": msc, "value": Sc * Nc / (msc * 1e-3),
-                                "unit": "symbol*bars/s", "algorithmic_bytes_per_symbol_bar": 316, "achieved_gbs": gc,
-                                "frac": gc / peak}
+            return {"workload": "SURVEY 8f.1: 61 cdl* patterns + 4 price transforms + bop, 20,000 x 5,040 random-walk OHLC",
+                    "kernel": "candle_kernel<true>", "kernel_ms": msc, "value": Sc * Nc / (msc * 1e-3),
+                    "unit": "symbol*bars/s", "algorithmic_bytes_per_symbol_bar": 316, "achieved_gbs": gc, "frac": gc / peak}
+
+        def mix():
             # what HBM delivers for the suite's own access mix (4 planes read, 21 written, 256-byte warp rows) with no
             # arithmetic at all: the copy bandwidth used as `peak` is a 1 : 1 mix, a write-heavy stream gets less
             import ctypes as C
-            from polars_quant_b200 import _native as NN
             msx = C.c_float()
-            NN.check(NN.lib().pqb_stream_mix(engine._h, N_IN, N_OUT, 20_000 * 5_040, 2, 5, C.byref(msx)))
+            NV.check(NV.lib().pqb_stream_mix(engine._h, N_IN, N_OUT, 20_000 * 5_040, 2, 5, C.byref(msx)))
             gx = 8 * (N_IN + N_OUT) * 20_000 * 5_040 / (msx.value * 1e-3) / 1e9
-            other["access_mix_ceiling"] = {"workload": "streaming kernel, %d planes read : %d written, 20,000 x 5,040 doubles each, no arithmetic" % (N_IN, N_OUT),
-                                           "kernel": "stream_mix_kernel", "kernel_ms": msx.value, "achieved_gbs": gx, "frac": gx / peak,
-                                           "suite_over_mix": achieved / gx}
-        except Exception as ex:          # never lose the headline line to an extra
-            other["error"] = repr(ex)
+            return {"workload": "streaming kernel, %d planes read : %d written, 20,000 x 5,040 doubles each, no arithmetic" % (N_IN, N_OUT),
+                    "kernel": "stream_mix_kernel", "kernel_ms": msx.value, "achieved_gbs": gx, "frac": gx / peak,
+                    "suite_over_mix": achieved / gx}
+
+        if (S_total, N) != WORKLOADS["c2"][:2]:
+            extra("c2", c2)
+        extra("c4_one_of_8_gpus", shard8)
+        extra("c3", lambda: bench_c3(pq, NV, engine, peak))
+        extra("c5", lambda: bench_c5(pq, NV, engine, peak))
+        extra("candles", candle)
+        extra("access_mix_ceiling", mix)
 
     if rank == 0:
-        traffic = None
-        tp = ROOT / "profiles" / "traffic.json"
-        if tp.exists():
-            try:
-                tj = json.loads(tp.read_text())
-                if tj.get("symbols") == S and tj.get("bars") == N:
-                    traffic = tj.get("dram_bytes_per_launch")
-            except Exception:
-                pass
+        traffic, traffic_src = traffic_record(S, N)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": desc, "symbols_per_gpu": S, "bars": N, "indicators": 15, "outputs": N_OUT,
-                       "inputs": N_IN, "l2": "inputs+outputs per step (%.1f GB) are far larger than the 126 MB L2; no flush needed"
+            "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": desc, "symbols": S_total if args.scaling == "strong" else S_total * world,
+                       "symbols_per_gpu": S, "bars": N, "indicators": 15, "outputs": N_OUT,
+                       "inputs": N_IN, "l2": "inputs+outputs per step (%.1f GB per GPU) are far larger than the 126 MB L2; no flush needed"
                        % (ALGO_BYTES_PER_SYMBOL_BAR * S * N / 1e9),
-                       "parallelism": "symbols sharded per GPU, no collective"},
+                       "parallelism": "symbols sharded over the GPUs in contiguous 32-symbol blocks, no collective on the data path"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": "suite_fused_kernel<true,false>", "peak_source": peak_src,
+                         "traffic": traffic, "traffic_source": traffic_src,
+                         "kernel": "suite_fused_kernel<true,false>", "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": ALGO_BYTES_PER_SYMBOL_BAR * S * N,
-                         "kernel_ms": fused_ms_avg},
+                         "kernel_ms": fused_ms_avg, "per": "the slowest rank's launch over its own share of the panel"},
             "cpu_baseline": cpu,
             "e2e": e2e,
             "gpu_launches": launches * args.steps + e2e_launches,
@@ -373,7 +491,6 @@ def main():
         if other:
             line["other_workloads"] = other
         print(json.dumps(line), flush=True)
-    panel.close()
     if dist is not None:
         dist.destroy_process_group()
 

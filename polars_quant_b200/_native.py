@@ -70,6 +70,29 @@ class Col(C.Structure):
     _fields_ = [("values", C.c_void_p), ("validity", C.c_void_p), ("offset", C.c_int64), ("len", C.c_int64)]
 
 
+class ColRef(C.Structure):
+    """pqb_col_ref: one caller-owned Arrow f64 column and the (symbol, field) it goes to."""
+    _fields_ = [("values", C.c_void_p), ("validity", C.c_void_p), ("offset", C.c_int64), ("len", C.c_int64),
+                ("symbol", C.c_int64), ("field", C.c_int32), ("reserved", C.c_int32)]
+
+
+class ArrowSchema(C.Structure):
+    pass
+
+
+class ArrowArray(C.Structure):
+    pass
+
+
+ArrowSchema._fields_ = [("format", C.c_char_p), ("name", C.c_char_p), ("metadata", C.c_char_p), ("flags", C.c_int64),
+                        ("n_children", C.c_int64), ("children", C.POINTER(C.POINTER(ArrowSchema))),
+                        ("dictionary", C.POINTER(ArrowSchema)), ("release", C.c_void_p), ("private_data", C.c_void_p)]
+ArrowArray._fields_ = [("length", C.c_int64), ("null_count", C.c_int64), ("offset", C.c_int64), ("n_buffers", C.c_int64),
+                       ("n_children", C.c_int64), ("buffers", C.POINTER(C.c_void_p)),
+                       ("children", C.POINTER(C.POINTER(ArrowArray))), ("dictionary", C.POINTER(ArrowArray)),
+                       ("release", C.c_void_p), ("private_data", C.c_void_p)]
+
+
 class OutCol(C.Structure):
     _fields_ = [("values", C.c_void_p), ("validity", C.c_void_p)]
 
@@ -119,6 +142,15 @@ def lib() -> C.CDLL:
         L.pqb_panel_sync.argtypes = [C.c_void_p]
         L.pqb_suite_run.argtypes = [C.c_void_p, C.POINTER(SuiteParams)]
         L.pqb_suite_run_host.argtypes = [C.c_void_p, C.POINTER(SuiteParams), C.c_int64]
+        L.pqb_panel_set_columns.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int]
+        L.pqb_suite_run_columns.argtypes = [C.c_void_p, C.POINTER(SuiteParams), C.c_void_p, C.c_int64, C.c_int]
+        L.pqb_panel_set_record_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.pqb_suite_run_record_batch.argtypes = [C.c_void_p, C.POINTER(SuiteParams), C.c_void_p, C.c_void_p, C.c_void_p,
+                                                 C.c_void_p, C.c_int]
+        L.pqb_panel_export_arrow.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.pqb_output_name.argtypes = [C.c_int]
+        L.pqb_output_name.restype = C.c_char_p
+        L.pqb_engine_local_cpus.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         L.pqb_panel_get_output.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_int64]
         L.pqb_panel_fill_synthetic.argtypes = [C.c_void_p, C.c_uint64, C.c_double, C.c_int]
         L.pqb_suite_time.argtypes = [C.c_void_p, C.POINTER(SuiteParams), C.c_int, C.c_int, C.POINTER(C.c_float),

@@ -1596,18 +1596,46 @@ static int run_single(pqb_engine *e, const pqb_col *const *cols, const int *fiel
         e->scratch_bars = n;
     }
     pqb_panel *p = e->scratch;
-    for (int f = 0; f < PQB_N_FIELDS; ++f) memset(p->h_in[f], 0, (size_t)p->pitch * sizeof(double));
-    p->h_start[0] = 0;
     p->h_start_explicit[0] = 0;
-    p->starts_nonzero = false;
     p->h_flags[0] = 0;
     for (int f = 0; f < PQB_N_FIELDS; ++f) { p->h_lead[f][0] = -1; p->h_vin[f].clear(); }
-    for (int i = 0; i < n_cols; ++i)
+    uint32_t fmask = 0;
+    for (int i = 0; i < n_cols; ++i) {
         if ((rc = pqb_panel_set_column(p, 0, fields[i], cols[i]->values, cols[i]->validity, cols[i]->offset, n))) return rc;
-    if ((rc = pqb_panel_upload(p))) return rc;
+        fmask |= 1u << fields[i];
+    }
+    // only what this call touches crosses PCIe: the given fields up, the requested outputs down (the scratch panel has
+    // every plane allocated; one EMA on a 1 M-bar column used to move 43 result planes)
+    cudaStream_t st = e->stream;
+    {
+        const double *rm[PQB_N_FIELDS];
+        double *tl[PQB_N_FIELDS];
+        int nf = 0;
+        const size_t cplane = (size_t)p->chunk_symbols * p->pitch;
+        for (int f = 0; f < PQB_N_FIELDS; ++f) {
+            if (!(fmask >> f & 1)) continue;
+            double *buf = p->d_xin[0] + cplane * p->in_slot[f];
+            CU(cudaMemcpyAsync(buf, p->h_in[f], (size_t)p->pitch * sizeof(double), cudaMemcpyHostToDevice, st));
+            rm[nf] = buf; tl[nf] = p->d_in[f]; ++nf;
+        }
+        if ((rc = launch_conv(p, true, rm, tl, nf, 0, 1, st))) return rc;
+        p->inputs_resident = true;
+        if ((rc = prepare_nulls(p, st))) return rc;
+    }
     if ((rc = pqb_suite_run(p, sp))) return rc;
-    if ((rc = pqb_panel_download(p))) return rc;
-    if ((rc = pqb_panel_sync(p))) return rc;
+    {
+        const double *rm[PQB_N_OUTPUTS];
+        double *tl[PQB_N_OUTPUTS];
+        const size_t cplane = (size_t)p->chunk_symbols * p->pitch;
+        for (int i = 0; i < n_out; ++i) { rm[i] = p->d_xout[0] + cplane * p->out_slot[outs[i]]; tl[i] = p->d_out[outs[i]]; }
+        if ((rc = launch_conv(p, false, rm, tl, n_out, 0, 1, st))) return rc;
+        for (int i = 0; i < n_out; ++i) {
+            CU(cudaMemcpyAsync(p->h_out[outs[i]], rm[i], (size_t)p->pitch * sizeof(double), cudaMemcpyDeviceToHost, st));
+            CU(cudaMemcpyAsync(p->h_bits[outs[i]], p->d_bits[outs[i]], (size_t)p->words_per_row * sizeof(uint32_t),
+                               cudaMemcpyDeviceToHost, st));
+        }
+    }
+    CU(cudaStreamSynchronize(st));
     for (int i = 0; i < n_out; ++i)
         if ((rc = pqb_panel_get_output(p, 0, outs[i], dst[i]->values, dst[i]->validity, n))) return rc;
     return PQB_OK;

@@ -33,6 +33,12 @@ class Engine:
     def flush_l2(self):
         N.check(N.lib().pqb_flush_l2(self._h))
 
+    def local_cpus(self):
+        """CPUs local to this engine's GPU (NVML affinity): where the engine pins its staging and runs its intake threads."""
+        buf = (C.c_int * 1024)()
+        n = N.lib().pqb_engine_local_cpus(self._h, buf, 1024)
+        return [buf[i] for i in range(min(n, 1024))]
+
 
 _engines: dict[int, Engine] = {}
 
@@ -70,28 +76,33 @@ class Panel:
             pass
 
     # ---- host staging views (zero-copy numpy over pinned memory) ----
+    def _view(self, ptr, ctype, count, dtype):
+        """numpy view of `count` elements of pinned staging.  The view (and every array sliced from it) holds a
+        reference to this Panel through its base buffer, so the pinned planes outlive a dropped Panel object -- they
+        return to the engine's pool only when the last view is gone.  An explicit close() still invalidates views."""
+        buf = (ctype * count).from_address(ptr)
+        buf._owner = self
+        return np.frombuffer(buf, dtype=dtype)
+
     def host_field(self, field) -> np.ndarray:
         f = self.FIELDS[field] if isinstance(field, str) else field
         ptr = N.lib().pqb_panel_host_field(self._h, f)
         if not ptr:
             raise ValueError("panel has no host staging for field %r" % (field,))
-        buf = (C.c_double * (self.n_symbols * self.pitch)).from_address(ptr)
-        return np.frombuffer(buf, dtype=np.float64).reshape(self.n_symbols, self.pitch)
+        return self._view(ptr, C.c_double, self.n_symbols * self.pitch, np.float64).reshape(self.n_symbols, self.pitch)
 
     def host_output(self, k: int) -> np.ndarray:
         ptr = N.lib().pqb_panel_host_output(self._h, k)
         if not ptr:
-            raise ValueError("output %d not allocated" % k)
-        buf = (C.c_double * (self.n_symbols * self.pitch)).from_address(ptr)
-        return np.frombuffer(buf, dtype=np.float64).reshape(self.n_symbols, self.pitch)[:, :self.n_bars]
+            raise ValueError("output %d is not allocated (or the panel has no host staging)" % k)
+        return self._view(ptr, C.c_double, self.n_symbols * self.pitch, np.float64).reshape(self.n_symbols, self.pitch)[:, :self.n_bars]
 
     def host_validity(self, k: int) -> np.ndarray:
         """bool [n_symbols, n_bars] unpacked from the Arrow LSB-first bitmaps."""
         ptr = N.lib().pqb_panel_host_validity(self._h, k)
         if not ptr:
-            raise ValueError("output %d not allocated" % k)
-        buf = (C.c_uint8 * (self.n_symbols * self.validity_pitch)).from_address(ptr)
-        bits = np.frombuffer(buf, dtype=np.uint8).reshape(self.n_symbols, self.validity_pitch)
+            raise ValueError("output %d is not allocated (or the panel has no host staging)" % k)
+        bits = self._view(ptr, C.c_uint8, self.n_symbols * self.validity_pitch, np.uint8).reshape(self.n_symbols, self.validity_pitch)
         return np.unpackbits(bits, axis=1, bitorder="little")[:, :self.n_bars].astype(bool)
 
     # ---- loading ----
@@ -120,6 +131,63 @@ class Panel:
 
     def fill_synthetic(self, seed: int = 0xC0FFEE, sigma: float = 0.02, to_host: bool = False):
         N.check(N.lib().pqb_panel_fill_synthetic(self._h, seed, sigma, 1 if to_host else 0))
+
+    @staticmethod
+    def col_refs(columns):
+        """[(symbol, field, values float64 ndarray, validity packed-bitmap uint8 ndarray | None), ...] -> a ctypes array
+        of pqb_col_ref (+ the list of arrays it borrows from: keep it alive as long as the refs are used)."""
+        refs = (N.ColRef * len(columns))()
+        keep = []
+        for r, (symbol, field, values, validity) in zip(refs, columns):
+            v = np.ascontiguousarray(values, dtype=np.float64)
+            keep.append(v)
+            r.values, r.offset, r.len, r.symbol = v.ctypes.data, 0, v.size, symbol
+            r.field = Panel.FIELDS[field] if isinstance(field, str) else int(field)
+            if validity is not None:
+                b = np.ascontiguousarray(validity, dtype=np.uint8)
+                keep.append(b)
+                r.validity = b.ctypes.data
+        return refs, keep
+
+    @staticmethod
+    def field_refs(close=None, high=None, low=None, volume=None):
+        """pqb_col_ref array for dense [n_symbols, n_bars] float64 field matrices (C-contiguous rows), built without a
+        Python loop: one ref per (symbol, field) pointing into the caller's own memory."""
+        mats = [(f, np.ascontiguousarray(a, dtype=np.float64)) for f, a in
+                ((N.CLOSE, close), (N.HIGH, high), (N.LOW, low), (N.VOLUME, volume)) if a is not None]
+        S, nb = mats[0][1].shape
+        rec = np.zeros(S * len(mats), dtype=np.dtype([("values", np.uint64), ("validity", np.uint64), ("offset", np.int64),
+                                                      ("len", np.int64), ("symbol", np.int64), ("field", np.int32),
+                                                      ("reserved", np.int32)]))
+        for i, (f, a) in enumerate(mats):
+            sl = rec[i * S:(i + 1) * S]
+            sl["values"] = a.ctypes.data + np.arange(S, dtype=np.uint64) * np.uint64(a.strides[0])
+            sl["len"], sl["symbol"], sl["field"] = nb, np.arange(S), f
+        return rec, [a for _, a in mats]
+
+    def set_columns(self, refs, n=None, threads: int = 0):
+        """Batch intake (pqb_panel_set_columns): `refs` from col_refs() / field_refs()."""
+        ptr, n = (refs.ctypes.data, len(refs)) if isinstance(refs, np.ndarray) else (C.addressof(refs), len(refs) if n is None else n)
+        N.check(N.lib().pqb_panel_set_columns(self._h, ptr, n, threads))
+
+    def run_columns(self, refs, params: N.SuiteParams | None = None, threads: int = 0):
+        """Caller-owned columns in, results in the pinned result planes: intake pipelined with H2D / suite / D2H
+        (pqb_suite_run_columns)."""
+        params = params or N.default_params()
+        ptr, n = (refs.ctypes.data, len(refs)) if isinstance(refs, np.ndarray) else (C.addressof(refs), len(refs))
+        N.check(N.lib().pqb_suite_run_columns(self._h, C.byref(params), ptr, n, threads))
+
+    def export_arrow(self, outputs_mask: int = 0, symbol_names=None):
+        """Every result column of the last run as ONE pyarrow RecordBatch (`{symbol}_{output}` Float64 columns aliasing
+        the pinned result planes; the batch keeps the native panel alive)."""
+        import pyarrow as pa
+        arr, sch = N.ArrowArray(), N.ArrowSchema()
+        names = None
+        if symbol_names is not None:
+            enc = [s.encode() for s in symbol_names]
+            names = (C.c_char_p * len(enc))(*enc)
+        N.check(N.lib().pqb_panel_export_arrow(self._h, outputs_mask, names, C.byref(arr), C.byref(sch)))
+        return pa.RecordBatch._import_from_c(C.addressof(arr), C.addressof(sch))
 
     # ---- running ----
     def upload(self):
@@ -164,8 +232,9 @@ class Panel:
         res = {}
         for q, name in enumerate(self.SIGNALS):
             ptr = N.lib().pqb_panel_host_signal(self._h, q)
-            buf = (C.c_int8 * (self.n_symbols * self.pitch)).from_address(ptr)
-            res[name] = np.frombuffer(buf, dtype=np.int8).reshape(self.n_symbols, self.pitch)[:, :self.n_bars]
+            if not ptr:
+                raise ValueError("signals need a panel with host staging")
+            res[name] = self._view(ptr, C.c_int8, self.n_symbols * self.pitch, np.int8).reshape(self.n_symbols, self.pitch)[:, :self.n_bars]
         return res
 
     def info(self):

@@ -33,6 +33,8 @@ def run_sharded(close, high, low, volume, params=None, starts=None, dist=None, d
     of the row-major host panel [n_symbols, n_bars] and returns (lo, hi, outputs) for that range.
     `dist` = an initialised torch.distributed module (or None for a single process); it is used only
     to learn rank/world -- there is no collective on the data path."""
+    import os
+    from . import _native as N
     from .panel import Panel, get_engine
     rank = dist.get_rank() if dist is not None else 0
     world = dist.get_world_size() if dist is not None else 1
@@ -40,7 +42,11 @@ def run_sharded(close, high, low, volume, params=None, starts=None, dist=None, d
     lo, hi = symbol_range(n_symbols, world, rank)
     if hi == lo:
         return lo, hi, {}
-    eng = get_engine(device if device is not None else 0)
+    if device is None:
+        # one process per GPU: the rank's own device (torchrun's LOCAL_RANK), never everyone on GPU 0
+        n_dev = max(1, N.lib().pqb_device_count())
+        device = int(os.environ.get("LOCAL_RANK", rank)) % n_dev
+    eng = get_engine(device)
     p = Panel(hi - lo, n_bars, engine=eng)
     p.set_fields(close[lo:hi], None if high is None else high[lo:hi], None if low is None else low[lo:hi],
                  None if volume is None else volume[lo:hi], starts=None if starts is None else starts[lo:hi])

@@ -26,7 +26,7 @@ import pyarrow.compute as pc
 
 from . import _native as N
 from .candles import CandlePanel, default_params as candle_default_params, pattern_names
-from .panel import Engine, Panel
+from .panel import Engine, Panel, get_engine
 
 SUITE_FIELDS = ("close", "high", "low", "volume")          # enum pqb_field order
 CANDLE_FIELDS = ("open", "high", "low", "close")           # enum pqb_candle_field order
@@ -219,44 +219,105 @@ class WidePanel:
         self._index = {name: i for i, name in enumerate(table.column_names)}     # (Table[name] is slow on wide tables)
         self._suite = None
         self._candles = None
+        self._batch = None
 
     def _col(self, name):
         return self.table.column(self._index[name])
 
     # ---- the 15-indicator suite (+ optional groups through `params.indicators`) ----
-    def suite(self, params: N.SuiteParams | None = None, outputs=None) -> pa.Table:
+    def _suite_map(self, symbols, cols):
+        """column index -> (symbol row, field) arrays for pqb_*_record_batch (field -1: not a panel column)."""
+        sym = np.zeros(self.table.num_columns, dtype=np.int64)
+        fld = np.full(self.table.num_columns, -1, dtype=np.int32)
+        for f, fname in enumerate(SUITE_FIELDS):
+            by = cols[fname]
+            idx = np.fromiter((self._index[by[s]] for s in symbols), dtype=np.int64, count=len(symbols))
+            sym[idx] = np.arange(len(symbols))
+            fld[idx] = f
+        return sym, fld
+
+    def _record_batch(self):
+        """The table as ONE record batch exported through the Arrow C Data Interface (zero copy for a single-chunk table)."""
+        if self._batch is None:
+            t = self.table if all(c.num_chunks <= 1 for c in self.table.columns) else self.table.combine_chunks()
+            batches = t.to_batches()
+            self._batch = batches[0] if batches else pa.RecordBatch.from_pylist([], schema=t.schema)
+        arr, sch = N.ArrowArray(), N.ArrowSchema()
+        self._batch._export_to_c(C.addressof(arr), C.addressof(sch))
+        return arr, sch
+
+    @staticmethod
+    def _release(arr, sch):
+        for x, proto in ((arr, C.CFUNCTYPE(None, C.POINTER(N.ArrowArray))), (sch, C.CFUNCTYPE(None, C.POINTER(N.ArrowSchema)))):
+            if x.release:
+                proto(x.release)(C.pointer(x))
+
+    def suite(self, params: N.SuiteParams | None = None, outputs=None, threads: int = 0, devices=None) -> pa.Table:
         """Runs the fused suite over every symbol that has close / high / low / volume columns; returns `date` +
-        `{symbol}_{output}` for the requested output names (default: the 21 suite outputs)."""
+        `{symbol}_{output}` for the requested output names (default: the 21 suite outputs).  The table crosses the C ABI
+        as ONE Arrow record batch (pqb_suite_run_record_batch: intake pipelined with the GPU pipeline) and the results
+        come back as ONE record batch aliasing the pinned result planes (pqb_panel_export_arrow) -- no per-column work in
+        Python.  `devices`: GPU ordinals to shard the symbols over (contiguous ranges, one host thread per GPU, no
+        collective -- SURVEY.md 8e); default: this panel's engine only."""
         symbols, cols = split_columns(self.table, SUITE_FIELDS)
         symbols = [s for s in symbols if all(s in cols[f] for f in SUITE_FIELDS)]
         if not symbols:
             raise ValueError("no symbol has all of " + ", ".join("{symbol}_" + f for f in SUITE_FIELDS))
         params = params or N.default_params()
         names = list(outputs) if outputs is not None else N.OUTPUT_NAMES[:N.N_SUITE_OUTPUTS]
-        ks = [N.OUTPUT_NAMES.index(n) for n in names]
-        omask = sum(1 << k for k in ks)
+        omask = sum(1 << N.OUTPUT_NAMES.index(n) for n in names)
         self._suite = None          # (an earlier panel no result refers to any more goes back to the engine's pinned pool first)
-        p = Panel(len(symbols), self.n_bars, engine=self.engine, outputs_mask=omask)
-        keep = []
-        for s, sym in enumerate(symbols):
-            for f, fname in enumerate(SUITE_FIELDS):
-                arr = _f64(self._col(cols[fname][sym]))
-                keep.append(arr)
-                _set(N.lib().pqb_panel_set_column, p._h, s, f, arr, self.n_bars)
-        p.run_host(params)
-        self._suite = p
-        base = _Keep(p)
-        out_cols, out_names = ([self.dates], ["date"]) if self.dates is not None else ([], [])
-        vbytes = (self.n_bars + 7) // 8
-        for s, sym in enumerate(symbols):
-            for k, n in zip(ks, names):
-                vals = N.lib().pqb_panel_host_output(p._h, k) + s * p.pitch * 8
-                bits = N.lib().pqb_panel_host_validity(p._h, k) + s * p.validity_pitch
-                arr = pa.Array.from_buffers(pa.float64(), self.n_bars,
-                                            [pa.foreign_buffer(bits, vbytes, base), pa.foreign_buffer(vals, self.n_bars * 8, base)])
-                out_cols.append(arr)
-                out_names.append("%s_%s" % (sym, n))
-        return pa.table(out_cols, names=out_names)
+        sym, fld = self._suite_map(symbols, cols)
+        engines = [self.engine or get_engine(0)] if not devices else [get_engine(d) for d in devices]
+        from .shard import symbol_range
+        shards = []
+        for g, eng in enumerate(engines):
+            lo, hi = symbol_range(len(symbols), len(engines), g)
+            if hi > lo:
+                shards.append((eng, lo, hi))
+        batches = [None] * len(shards)
+        errors = []
+
+        def run(i):
+            eng, lo, hi = shards[i]
+            try:
+                p = Panel(hi - lo, self.n_bars, engine=eng, outputs_mask=omask)
+                mine = (fld >= 0) & (sym >= lo) & (sym < hi)
+                s_i = np.ascontiguousarray(np.where(mine, sym - lo, 0), dtype=np.int64)
+                f_i = np.ascontiguousarray(np.where(mine, fld, -1), dtype=np.int32)
+                arr, sch = self._record_batch()
+                try:
+                    N.check(N.lib().pqb_suite_run_record_batch(p._h, C.byref(params), C.byref(arr), C.byref(sch), s_i.ctypes.data,
+                                                               f_i.ctypes.data, threads))
+                finally:
+                    self._release(arr, sch)
+                batches[i] = (p, p.export_arrow(omask, symbols[lo:hi]))
+            except Exception as ex:                      # (raised again on the calling thread)
+                errors.append(ex)
+
+        if len(shards) == 1:
+            run(0)
+        else:
+            import threading
+            ts = [threading.Thread(target=run, args=(i,)) for i in range(len(shards))]
+            for t in ts:
+                t.start()
+            for t in ts:
+                t.join()
+        if errors:
+            raise errors[0]
+        self._suite = [p for p, _ in batches]
+        if len(batches) == 1:
+            out = pa.Table.from_batches([batches[0][1]])
+        else:
+            out_cols, out_names = [], []
+            for _, rb in batches:
+                out_cols.extend(rb.columns)
+                out_names.extend(rb.schema.names)
+            out = pa.table(out_cols, names=out_names)
+        if self.dates is not None:
+            out = out.add_column(0, "date", self.dates)
+        return out
 
     # ---- Selector.info(): last-row reductions (README.md:832-851) ----
     def info(self) -> pa.Table:
@@ -268,12 +329,12 @@ class WidePanel:
         if not symbols:
             raise ValueError("no symbol has all of " + ", ".join("{symbol}_" + f for f in SUITE_FIELDS))
         p = Panel(len(symbols), self.n_bars, engine=self.engine, outputs_mask=1)
-        keep = []
-        for s, sym in enumerate(symbols):
-            for f, fname in enumerate(SUITE_FIELDS):
-                arr = _f64(self._col(cols[fname][sym]))
-                keep.append(arr)
-                _set(N.lib().pqb_panel_set_column, p._h, s, f, arr, self.n_bars)
+        sym_i, fld_i = self._suite_map(symbols, cols)
+        arr, sch = self._record_batch()
+        try:
+            N.check(N.lib().pqb_panel_set_record_batch(p._h, C.byref(arr), C.byref(sch), sym_i.ctypes.data, fld_i.ctypes.data, 0))
+        finally:
+            self._release(arr, sch)
         p.upload()
         res = p.info()
         last = self.n_bars - 1
