@@ -192,6 +192,15 @@ def lib() -> C.CDLL:
         L.pqb_split_run_host.argtypes = [C.c_void_p, C.POINTER(SuiteParams)]
         L.pqb_split_get_output.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_int64]
         L.pqb_split_fill_synthetic.argtypes = [C.c_void_p, C.c_uint64, C.c_double]
+        # long rows (config 3)
+        L.pqb_long_create.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int64, C.c_int, C.POINTER(C.c_void_p)]
+        L.pqb_long_destroy.argtypes = [C.c_void_p]
+        L.pqb_long_destroy.restype = None
+        L.pqb_long_panel.argtypes = [C.c_void_p]
+        L.pqb_long_panel.restype = C.c_void_p
+        L.pqb_long_run.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int32, C.c_int32, C.c_int32]
+        L.pqb_long_last_launches.argtypes = [C.c_void_p]
+        L.pqb_long_time.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int32, C.c_int32, C.c_int32, C.c_int, C.c_int, C.POINTER(C.c_float)]
         # candle engine
         L.pqb_candle_params_default.argtypes = [C.POINTER(CandleParams)]
         L.pqb_candle_params_default.restype = None

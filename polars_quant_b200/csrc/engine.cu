@@ -11,6 +11,7 @@
 #include "../../include/pqb200_polars_plugin.h"   // the Arrow C Data Interface structs
 #include "suite_kernel.cuh"
 #include "candles.cuh"
+#include "longrows.cuh"
 
 #include <algorithm>
 #include <atomic>
@@ -721,7 +722,7 @@ static int build_args(const pqb_panel *p, const pqb_suite_params *sp, Built *out
     A.don_fold = 0; A.don_p = 1;
     // the arguments of the PLAIN kernels; launch_suite derives the null-aware variant (null_variant) for the symbol
     // blocks that need it
-    A.start = p->starts_nonzero ? p->d_start : nullptr;
+    A.start = p->d_start;      // (always: with pipelined intake the starts reach the device after these arguments are built)
     A.vmask = nullptr;
     A.symflags = nullptr;
     A.blist = nullptr;
@@ -1940,5 +1941,6 @@ extern "C" int pqb_multi_run_host(pqb_multi *m, const pqb_suite_params *params) 
 #include "columns_host.inc"
 #include "candles_host.inc"
 #include "split_host.inc"
+#include "longrows_host.inc"
 #include "signals_host.inc"
 #include "info_host.inc"

@@ -1,0 +1,228 @@
+// longrows.cuh -- few symbols, very long rows (BASELINE config 3: 500 symbols x 1,000,000 minute bars): K exponential
+// moving averages + MACD in ONE pass over close, parallel along TIME.
+//
+// The fused suite kernel walks a symbol's time axis serially; 500 symbols are 16 symbol blocks for 444 CTA slots.  The
+// EMA family (calc_ema overlap.rs:660-730, macd momentum.rs:250-283) is a chain of affine maps
+//     y_t = (1 - alpha) * y_{t-1} + alpha * x_t          (the reference evaluates it as alpha.mul_add(x - y, y))
+// so a row is cut into tiles of L bars and the state is carried across tiles by composing the tiles' maps
+// (north_star: "affine-composition scans for the EMA, MACD and Wilder-RSI recurrences"):
+//   seed   (lr_seed_kernel)   per chain: the reference's seed = (x_0 + ... + x_{p-1}) / p, summed left to right like
+//                             the reference, emitted at bar p-1
+//   local  (lr_local_kernel)  per (tile, symbol block): the tile's end state from a ZERO start, B_k (the tile's affine
+//                             map is y -> A y + B_k with the same A = (1 - alpha)^L for every tile); for the MACD signal
+//                             line, an EMA of dif = fast - slow, the local part from the local fast / slow states
+//   carry  (lr_carry_kernel)  per symbol: y_k = A y_{k-1} + B_k over the tiles (977 steps of one fma at config 3); the
+//                             signal's carry adds Cf * fast_{k-1} - Cs * slow_{k-1}, the closed-form contribution of the
+//                             fast / slow start states to the tile's dif values
+//   final  (lr_final_kernel)  per (tile, symbol block): starts from the carried state and walks the tile's bars in the
+//                             REFERENCE'S OWN operation order (fma(alpha, x - y, y), dif = f - s, hist = dif - signal),
+//                             writing every output once
+// Tile 0 (and the tile that holds a chain's seed bar) is the reference's computation itself; later tiles differ from the
+// serial walk only through the rounding of the carried start state (a few ulp of the state, i.e. relative 1e-15 of the
+// price level), inside the north-star tolerance (rel 1e-10 / abs 1e-12) -- tolerance-exact, not bit-exact, like the
+// time-split panels of split_host.inc, but with no warm-up recomputation: 72 B of traffic per symbol-bar (close read
+// twice) against 64 B algorithmic, whatever the period.
+// Layout: the tiled planes of suite_kernel.cuh ([symbol block][bar][32 symbols]); lane = symbol, one warp = one
+// (tile, block) unit reading / writing 256 contiguous bytes per plane per bar.
+#pragma once
+#include "suite_kernel.cuh"
+
+namespace pqb {
+
+constexpr int LR_MAX_CH = 8;      // distinct EMA chains of one launch (the MACD fast / slow EMAs share a chain with an equal period)
+constexpr int LR_MAX_EMA = 7;     // EMA output planes
+constexpr int LR_BATCH = 16;      // bars loaded ahead per lane
+
+struct LongArgs {
+    const double *x;                   // close, tiled
+    double *chain_out[LR_MAX_CH];      // tiled output plane of chain c's EMA, or nullptr (a chain that only feeds the MACD)
+    double *macd_out[3];               // macd, macd_signal, macd_hist
+    int macd;                          // MACD on: chains 0 and 1 are its fast and slow EMA (fixed slots: registers, no indexing)
+    int n_ch;                          // distinct chains
+    int p[LR_MAX_CH];                  // period
+    double alpha[LR_MAX_CH];           // 2 / (p + 1)                     overlap.rs:669
+    double A[LR_MAX_CH];               // (1 - alpha)^L
+    int macd_f, macd_s, macd_g;
+    double alpha_g, A_g, Cf, Cs;       // signal chain: alpha, (1 - alpha_g)^L, start-state couplings (see lr_carry_kernel)
+    double *seed;                      // [n_ch][n_blocks * 32]
+    double *agg;                       // [n_tiles][n_ch + 1][n_blocks * 32]: B_k, then (in place) the carried end states
+    int n_symbols, n_bars, n_blocks, bars_padded, L, n_tiles;
+};
+
+__device__ __forceinline__ double ld_stream(const double *p) { return __ldcs(p); }
+
+// ---- seed: one warp per (symbol block, chain) -------------------------------------------------------------------------
+__global__ void __launch_bounds__(32) lr_seed_kernel(const __grid_constant__ LongArgs A) {
+    const int lane = threadIdx.x, b = blockIdx.x, c = blockIdx.y;
+    const int p = A.p[c];
+    const double *x = A.x + (size_t)b * A.bars_padded * SYM + lane;
+    double sum = 0.0;
+    if (p <= A.n_bars)
+        for (int t = 0; t < p; ++t) sum += x[(size_t)t * SYM];          // left to right, like the reference (:689-693)
+    A.seed[(size_t)c * A.n_blocks * SYM + b * SYM + lane] = sum / (double)p;       // :696
+}
+
+// the state of the MACD lines in tile 0: the reference's own count-based logic (Ema::step of suite_kernel.cuh)
+struct MacdHead {
+    Ema mf, ms, mg;
+    __device__ __forceinline__ void init() { mf.init(); ms.init(); mg.init(); }
+    __device__ __forceinline__ void step(const LongArgs &A, double c, int t, double &dif, double &sig, bool &okd, bool &okg) {
+        const bool okf = mf.step<false>(c, t, A.macd_f, A.alpha[0]);
+        const bool oks = ms.step<false>(c, t, A.macd_s, A.alpha[1]);
+        okd = okf && oks;
+        dif = mf.y - ms.y;                                               // momentum.rs:264
+        okg = mg.step<false>(okd ? dif : 0.0, t, A.macd_g, A.alpha_g);   // unwrap_or(0.0) :269
+        sig = mg.y;
+    }
+};
+
+// ---- local: the end state of every chain over one tile from a zero start ---------------------------------------------------
+template <bool MACD>
+__global__ void __launch_bounds__(128) lr_local_kernel(const __grid_constant__ LongArgs A) {
+    const int lane = threadIdx.x & 31;
+    const long long unit = (long long)blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (unit >= (long long)A.n_tiles * A.n_blocks) return;
+    const int tt = (int)(unit / A.n_blocks), b = (int)(unit % A.n_blocks);      // time-major: neighbouring warps share a tile index
+    const int t0 = tt * A.L, t1 = min(t0 + A.L, A.n_bars);
+    const double *x = A.x + ((size_t)b * A.bars_padded + t0) * SYM + lane;
+    const size_t lanes = (size_t)A.n_blocks * SYM;
+    double *out = A.agg + (size_t)tt * (A.n_ch + 1) * lanes + b * SYM + lane;
+    double y[LR_MAX_CH];
+    int from[LR_MAX_CH];                   // first bar of the tile at which chain c runs its recurrence
+#pragma unroll
+    for (int c = 0; c < LR_MAX_CH; ++c) {
+        y[c] = 0.0;
+        from[c] = t0;
+        if (c < A.n_ch) {
+            const int ts = A.p[c] - 1;     // the seed bar
+            if (ts >= t1) from[c] = t1;                                   // tile entirely before the seed: nothing
+            else if (ts >= t0) { from[c] = ts + 1; y[c] = A.seed[(size_t)c * lanes + b * SYM + lane]; }
+        }
+    }
+    MacdHead head;
+    double g = 0.0;
+    if (MACD && tt == 0) head.init();
+    for (int tb = t0; tb < t1; tb += LR_BATCH) {
+        double xv[LR_BATCH];
+#pragma unroll
+        for (int i = 0; i < LR_BATCH; ++i) xv[i] = (tb + i < t1) ? ld_stream(x + (size_t)(tb - t0 + i) * SYM) : 0.0;
+#pragma unroll
+        for (int i = 0; i < LR_BATCH; ++i) {
+            const int t = tb + i;
+            if (t >= t1) break;
+#pragma unroll
+            for (int c = 0; c < LR_MAX_CH; ++c)
+                if (c < A.n_ch && t >= from[c]) y[c] = fma(A.alpha[c], xv[i] - y[c], y[c]);
+            if (MACD) {
+                if (tt == 0) {
+                    double dif, sig; bool okd, okg;
+                    head.step(A, xv[i], t, dif, sig, okd, okg);
+                    g = sig;
+                } else {
+                    const double dif = y[0] - y[1];
+                    g = fma(A.alpha_g, dif - g, g);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < LR_MAX_CH; ++c)
+        if (c < A.n_ch) out[(size_t)c * lanes] = y[c];
+    out[(size_t)A.n_ch * lanes] = g;
+}
+
+// ---- carry: one thread per symbol, serial over the tiles ------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) lr_carry_kernel(const __grid_constant__ LongArgs A) {
+    const size_t lanes = (size_t)A.n_blocks * SYM;
+    const size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= lanes) return;
+    double y[LR_MAX_CH], g = 0.0;
+    int seed_tile[LR_MAX_CH];
+#pragma unroll
+    for (int c = 0; c < LR_MAX_CH; ++c) { y[c] = 0.0; seed_tile[c] = (c < A.n_ch) ? (A.p[c] - 1) / A.L : 0; }
+    const bool macd = A.macd != 0;
+    for (int tt = 0; tt < A.n_tiles; ++tt) {
+        double *rec = A.agg + (size_t)tt * (A.n_ch + 1) * lanes + s;
+        // the signal line first: it needs the fast / slow states at the START of this tile.  With f_j = f_loc_j +
+        // af^(j+1) f0 (and the same for s), dif_j = dif_loc_j + af^(j+1) f0 - as^(j+1) s0, and the signal's end state is
+        // linear in its inputs: g_end = Ag g0 + g_loc_end + Cf f0 - Cs s0, Cf = alpha_g * sum_j (1 - alpha_g)^(L-1-j) af^(j+1)
+        if (macd) {
+            const double bg = rec[(size_t)A.n_ch * lanes];
+            if (tt == 0) g = bg;
+            else g = fma(A.A_g, g, bg) + (A.Cf * y[0] - A.Cs * y[1]);
+            rec[(size_t)A.n_ch * lanes] = g;
+        }
+#pragma unroll
+        for (int c = 0; c < LR_MAX_CH; ++c) {
+            if (c >= A.n_ch) continue;
+            const double bk = rec[(size_t)c * lanes];
+            if (tt < seed_tile[c]) y[c] = 0.0;
+            else if (tt == seed_tile[c]) y[c] = bk;                      // the tile that holds the seed bar starts from the seed
+            else y[c] = fma(A.A[c], y[c], bk);
+            rec[(size_t)c * lanes] = y[c];
+        }
+    }
+}
+
+// ---- final: every output of one tile from the carried start state, in the reference's operation order ---------------------------
+template <bool MACD>
+__global__ void __launch_bounds__(128) lr_final_kernel(const __grid_constant__ LongArgs A) {
+    const int lane = threadIdx.x & 31;
+    const long long unit = (long long)blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (unit >= (long long)A.n_tiles * A.n_blocks) return;
+    const int tt = (int)(unit / A.n_blocks), b = (int)(unit % A.n_blocks);
+    const int t0 = tt * A.L, t1 = min(t0 + A.L, A.n_bars);
+    const size_t base = ((size_t)b * A.bars_padded + t0) * SYM + lane;
+    const double *x = A.x + base;
+    const size_t lanes = (size_t)A.n_blocks * SYM;
+    const double *prev = A.agg + (size_t)(tt > 0 ? tt - 1 : 0) * (A.n_ch + 1) * lanes + b * SYM + lane;
+    double y[LR_MAX_CH];
+    int from[LR_MAX_CH];                   // first bar of the tile at which chain c runs its recurrence; its first value is at from - 1
+#pragma unroll
+    for (int c = 0; c < LR_MAX_CH; ++c) {
+        y[c] = 0.0;
+        from[c] = t0;
+        if (c < A.n_ch) {
+            const int ts = A.p[c] - 1;
+            if (ts >= t1) from[c] = 0x7fffffff;                           // all null in this tile
+            else if (ts >= t0) { from[c] = ts + 1; y[c] = A.seed[(size_t)c * lanes + b * SYM + lane]; }
+            else y[c] = prev[(size_t)c * lanes];
+        }
+    }
+    MacdHead head;
+    double g = 0.0;
+    if (MACD) { if (tt == 0) head.init(); else g = prev[(size_t)A.n_ch * lanes]; }
+    const double nn = qnan();
+    for (int tb = t0; tb < t1; tb += LR_BATCH) {
+        double xv[LR_BATCH];
+#pragma unroll
+        for (int i = 0; i < LR_BATCH; ++i) xv[i] = (tb + i < t1) ? ld_stream(x + (size_t)(tb - t0 + i) * SYM) : 0.0;
+#pragma unroll
+        for (int i = 0; i < LR_BATCH; ++i) {
+            const int t = tb + i;
+            if (t >= t1) break;
+            const size_t o = base + (size_t)(t - t0) * SYM;
+#pragma unroll
+            for (int c = 0; c < LR_MAX_CH; ++c) {
+                if (c >= A.n_ch) continue;
+                if (t >= from[c]) y[c] = fma(A.alpha[c], xv[i] - y[c], y[c]);          // overlap.rs:698
+                if (A.chain_out[c]) stg(A.chain_out[c] + o, (t >= from[c] - 1) ? y[c] : nn);
+            }
+            if (MACD) {
+                double dif, sig;
+                bool okd = true, okg = true;
+                if (tt == 0) head.step(A, xv[i], t, dif, sig, okd, okg);
+                else {
+                    dif = y[0] - y[1];                                   // momentum.rs:264
+                    g = fma(A.alpha_g, dif - g, g);
+                    sig = g;
+                }
+                stg(A.macd_out[0] + o, okd ? dif : nn);
+                stg(A.macd_out[1] + o, okg ? sig : nn);
+                stg(A.macd_out[2] + o, (okd && okg) ? dif - sig : nn);   // :275
+            }
+        }
+    }
+}
+
+}  // namespace pqb

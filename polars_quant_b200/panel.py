@@ -64,10 +64,22 @@ class Panel:
         self.pitch = N.lib().pqb_panel_pitch(self._h)
         self.validity_pitch = N.lib().pqb_panel_validity_pitch(self._h)
 
+    @classmethod
+    def _borrowed(cls, handle, engine, n_symbols, n_bars, outputs_mask, host_staging, owner):
+        """A Panel over a native panel owned by another object (LongPanel, WindowPanel): same methods, never destroys."""
+        self = cls.__new__(cls)
+        self.engine, self.n_symbols, self.n_bars = engine, int(n_symbols), int(n_bars)
+        self.outputs_mask, self.host_staging = outputs_mask, host_staging
+        self._h = C.c_void_p(handle)
+        self._owner = owner
+        self.pitch = N.lib().pqb_panel_pitch(self._h)
+        self.validity_pitch = N.lib().pqb_panel_validity_pitch(self._h)
+        return self
+
     def close(self):
-        if self._h:
+        if self._h and getattr(self, "_owner", None) is None:
             N.lib().pqb_panel_destroy(self._h)
-            self._h = C.c_void_p()
+        self._h = C.c_void_p()
 
     def __del__(self):
         try:
