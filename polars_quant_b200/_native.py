@@ -201,6 +201,17 @@ def lib() -> C.CDLL:
         L.pqb_long_run.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int32, C.c_int32, C.c_int32]
         L.pqb_long_last_launches.argtypes = [C.c_void_p]
         L.pqb_long_time.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int32, C.c_int32, C.c_int32, C.c_int, C.c_int, C.POINTER(C.c_float)]
+        # many windows in one launch (config 5)
+        L.pqb_windows_create.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int, C.c_int32, C.c_int32, C.c_void_p,
+                                         C.c_int, C.c_int32, C.c_int, C.POINTER(C.c_void_p)]
+        L.pqb_windows_destroy.argtypes = [C.c_void_p]
+        L.pqb_windows_destroy.restype = None
+        L.pqb_windows_panel.argtypes = [C.c_void_p]
+        L.pqb_windows_panel.restype = C.c_void_p
+        L.pqb_windows_slot.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+        L.pqb_windows_run.argtypes = [C.c_void_p]
+        L.pqb_windows_last_launches.argtypes = [C.c_void_p]
+        L.pqb_windows_time.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_float)]
         # candle engine
         L.pqb_candle_params_default.argtypes = [C.POINTER(CandleParams)]
         L.pqb_candle_params_default.restype = None

@@ -12,6 +12,7 @@
 #include "suite_kernel.cuh"
 #include "candles.cuh"
 #include "longrows.cuh"
+#include "windows.cuh"
 
 #include <algorithm>
 #include <atomic>
@@ -1942,5 +1943,6 @@ extern "C" int pqb_multi_run_host(pqb_multi *m, const pqb_suite_params *params) 
 #include "candles_host.inc"
 #include "split_host.inc"
 #include "longrows_host.inc"
+#include "windows_host.inc"
 #include "signals_host.inc"
 #include "info_host.inc"

@@ -132,7 +132,10 @@ __global__ void __launch_bounds__(128) lr_local_kernel(const __grid_constant__ L
 }
 
 // ---- carry: one thread per symbol, serial over the tiles ------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) lr_carry_kernel(const __grid_constant__ LongArgs A) {
+// The loop-carried work is one fma per chain and tile; what would dominate is the latency of the loads of B_k, so they are
+// issued CB tiles ahead (independent of the chain), then consumed in order.
+constexpr int LR_CB = 8;
+__global__ void __launch_bounds__(64) lr_carry_kernel(const __grid_constant__ LongArgs A) {
     const size_t lanes = (size_t)A.n_blocks * SYM;
     const size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= lanes) return;
@@ -141,25 +144,38 @@ __global__ void __launch_bounds__(128) lr_carry_kernel(const __grid_constant__ L
 #pragma unroll
     for (int c = 0; c < LR_MAX_CH; ++c) { y[c] = 0.0; seed_tile[c] = (c < A.n_ch) ? (A.p[c] - 1) / A.L : 0; }
     const bool macd = A.macd != 0;
-    for (int tt = 0; tt < A.n_tiles; ++tt) {
-        double *rec = A.agg + (size_t)tt * (A.n_ch + 1) * lanes + s;
-        // the signal line first: it needs the fast / slow states at the START of this tile.  With f_j = f_loc_j +
-        // af^(j+1) f0 (and the same for s), dif_j = dif_loc_j + af^(j+1) f0 - as^(j+1) s0, and the signal's end state is
-        // linear in its inputs: g_end = Ag g0 + g_loc_end + Cf f0 - Cs s0, Cf = alpha_g * sum_j (1 - alpha_g)^(L-1-j) af^(j+1)
-        if (macd) {
-            const double bg = rec[(size_t)A.n_ch * lanes];
-            if (tt == 0) g = bg;
-            else g = fma(A.A_g, g, bg) + (A.Cf * y[0] - A.Cs * y[1]);
-            rec[(size_t)A.n_ch * lanes] = g;
-        }
+    const size_t stride = (size_t)(A.n_ch + 1) * lanes;
+    for (int tb = 0; tb < A.n_tiles; tb += LR_CB) {
+        double bk[LR_CB][LR_MAX_CH + 1];
 #pragma unroll
-        for (int c = 0; c < LR_MAX_CH; ++c) {
-            if (c >= A.n_ch) continue;
-            const double bk = rec[(size_t)c * lanes];
-            if (tt < seed_tile[c]) y[c] = 0.0;
-            else if (tt == seed_tile[c]) y[c] = bk;                      // the tile that holds the seed bar starts from the seed
-            else y[c] = fma(A.A[c], y[c], bk);
-            rec[(size_t)c * lanes] = y[c];
+        for (int i = 0; i < LR_CB; ++i)
+#pragma unroll
+            for (int c = 0; c <= LR_MAX_CH; ++c) {
+                const bool use = (tb + i < A.n_tiles) && (c < A.n_ch || (c == LR_MAX_CH && macd));
+                const int slot = (c == LR_MAX_CH) ? A.n_ch : c;
+                bk[i][c] = use ? __ldcg(A.agg + (size_t)(tb + i) * stride + (size_t)slot * lanes + s) : 0.0;
+            }
+#pragma unroll
+        for (int i = 0; i < LR_CB; ++i) {
+            const int tt = tb + i;
+            if (tt >= A.n_tiles) break;
+            double *rec = A.agg + (size_t)tt * stride + s;
+            // the signal line first: it needs the fast / slow states at the START of this tile.  With f_j = f_loc_j +
+            // af^(j+1) f0 (and the same for s), dif_j = dif_loc_j + af^(j+1) f0 - as^(j+1) s0, and the signal's end state is
+            // linear in its inputs: g_end = Ag g0 + g_loc_end + Cf f0 - Cs s0, Cf = alpha_g * sum_j (1 - alpha_g)^(L-1-j) af^(j+1)
+            if (macd) {
+                if (tt == 0) g = bk[i][LR_MAX_CH];
+                else g = fma(A.A_g, g, bk[i][LR_MAX_CH]) + (A.Cf * y[0] - A.Cs * y[1]);
+                rec[(size_t)A.n_ch * lanes] = g;
+            }
+#pragma unroll
+            for (int c = 0; c < LR_MAX_CH; ++c) {
+                if (c >= A.n_ch) continue;
+                if (tt < seed_tile[c]) y[c] = 0.0;
+                else if (tt == seed_tile[c]) y[c] = bk[i][c];                // the tile that holds the seed bar starts from the seed
+                else y[c] = fma(A.A[c], y[c], bk[i][c]);
+                rec[(size_t)c * lanes] = y[c];
+            }
         }
     }
 }

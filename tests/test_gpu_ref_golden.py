@@ -114,13 +114,17 @@ def test_gpu_reproduces_the_executed_reference(tag):
 
     g, index = refgolden.load()
     done = collections.Counter()
+    missing = []
     for e in index:
         if e["tag"] != tag or _branch_dependent(e):
             continue
         if e["fn"] in ("bop", "avgprice", "medprice", "typprice", "wclprice"):
             continue                                    # the candle engine's outputs: tests/test_gpu_candles.py
         name = f"{tag}/{e['key']}"
-        not_built = e["fn"] in NOT_BUILT or (e["fn"] == "ma" and e["kwargs"].get("matype") in NOT_BUILT_MATYPES)
+        if e["fn"] in NOT_BUILT:
+            done["defective_in_the_reference_not_built"] += 1      # no product function of that name (oracle-only)
+            continue
+        not_built = e["fn"] == "ma" and e["kwargs"].get("matype") in NOT_BUILT_MATYPES
         cols = refgolden.inputs(g, e)
         want = refgolden.expected(g, e)
         try:
@@ -138,6 +142,7 @@ def test_gpu_reproduces_the_executed_reference(tag):
             continue
         if got is None:
             done["no_entry_point"] += 1
+            missing.append(e["key"])
             continue
         assert not not_built, f"{name}: expected a refusal"
         if want is None:
@@ -154,4 +159,5 @@ def test_gpu_reproduces_the_executed_reference(tag):
         done["bit_exact"] += 1
     print(tag, dict(done))
     assert done["bit_exact"] + done["fails_alike"] >= 60, done
-    assert done["no_entry_point"] <= 3, done
+    # the only golden calls without a product entry point: STOCH with a non-SMA smoothing (matype != 0)
+    assert all(k.startswith("STOCH_14_5_1") for k in missing), missing
