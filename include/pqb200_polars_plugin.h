@@ -120,7 +120,10 @@ PQB_POLARS_PLUGIN(obv)       /* :70   (real, volume) */
 PQB_POLARS_PLUGIN(ad)        /* :19   (high, low, close, volume) */
 PQB_POLARS_PLUGIN(adosc)     /* :34   (high, low, close, volume; fastperiod=3, slowperiod=10) */
 /* Python-level compositions of the reference served as one call (python momentum.py:178-186) */
-PQB_POLARS_PLUGIN(stoch)     /* (high, low, close; fastk_period=5, slowk_period=3, slowd_period=3) -> struct stoch{slowk, slowd} */
+PQB_POLARS_PLUGIN(stoch)     /* :178 (high, low, close; fastk_period=5, slowk_period=3, slowk_matype=0, slowd_period=3, slowd_matype=0) -> struct stoch{slowk, slowd} */
+PQB_POLARS_PLUGIN(stochf)    /* :188 (high, low, close; fastk_period=5, fastd_period=3, fastd_matype=0) -> struct stochf{fastk, fastd} */
+PQB_POLARS_PLUGIN(stochrsi)  /* :197 (real; timeperiod=14, fastk_period=5, fastd_period=3, fastd_matype=0) -> struct stochrsi{fastk_rsi, fastd_rsi} */
+PQB_POLARS_PLUGIN(macdext)   /* :83  (real; fastperiod=12, fastmatype=0, slowperiod=26, slowmatype=0, signalperiod=9, signalmatype=0) -> struct macdext{macd_dif, macd_dea, macd_hist} */
 PQB_POLARS_PLUGIN(kdj)       /* (high, low, close; fastk_period=9, k_period=3, d_period=3) -> struct kdj{k, d, j} */
 
 /* the directional-movement family, momentum.rs; all (…; timeperiod=14) */

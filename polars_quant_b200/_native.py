@@ -11,7 +11,7 @@ _PKG = Path(__file__).resolve().parent
 LIB_PATH = Path(os.environ["PQB_LIB"]) if os.environ.get("PQB_LIB") else _PKG / "libpqb200.so"
 
 N_FIELDS = 4
-N_OUTPUTS = 43
+N_OUTPUTS = 44
 N_SUITE_OUTPUTS = 21      # the 15-indicator benchmark suite; 21.. = optional groups
 CLOSE, HIGH, LOW, VOLUME = 0, 1, 2, 3
 OUTPUT_NAMES = ["sma", "ema", "tema", "trima", "bb_upper", "bb_middle", "bb_lower", "macd",
@@ -19,7 +19,7 @@ OUTPUT_NAMES = ["sma", "ema", "tema", "trima", "bb_upper", "bb_middle", "bb_lowe
                 "kdj_k", "kdj_d", "kdj_j", "willr", "midprice",
                 "midpoint", "adosc", "mom", "roc", "rocp", "rocr", "rocr100", "cmo", "mfi", "cci",
                 "plus_dm", "minus_dm", "dx", "minus_di", "adx", "adxr", "trix", "ultosc", "aroon_up", "aroon_down",
-                "donchian_upper", "donchian_lower"]
+                "donchian_upper", "donchian_lower", "fastk"]
 IND = {"sma": 1 << 0, "ema": 1 << 1, "tema": 1 << 2, "trima": 1 << 3, "bbands": 1 << 4, "macd": 1 << 5,
        "rsi": 1 << 6, "trange": 1 << 7, "atr": 1 << 8, "natr": 1 << 9, "obv": 1 << 10, "ad": 1 << 11,
        "kdj": 1 << 12, "willr": 1 << 13, "midprice": 1 << 14}

@@ -830,6 +830,7 @@ static int build_args(const pqb_panel *p, const pqb_suite_params *sp, Built *out
             A.gmask |= G_KDJ; A.kdj_k = k; A.kdj_sk = sk; A.kdj_sd = sd; A.inv_sk = 1.0 / (double)sk; A.inv_sd = 1.0 / (double)sd;
             bind(PQB_OUT_KDJ_K, (long long)k + sk - 2); bind(PQB_OUT_KDJ_D, (long long)k + sk + sd - 3);
             bind(PQB_OUT_KDJ_J, (long long)k + sk + sd - 3);
+            if (want(PQB_OUT_FASTK)) { A.out[PQB_OUT_FASTK] = p->d_out[PQB_OUT_FASTK]; out->lead[PQB_OUT_FASTK] = NEVER; }   // validity from the kernel
             upto((long long)k + sk + sd - 2);
         }
     }
@@ -955,7 +956,7 @@ static uint64_t outputs_of_groups(unsigned g) {
     if (g & G_NATR) m |= 1u << 13;
     if (g & G_OBV) m |= 1u << 14;
     if (g & G_AD) m |= 1u << 15;
-    if (g & G_KDJ) m |= 7u << 16;
+    if (g & G_KDJ) m |= (7u << 16) | (1ull << 43);        // (fastk: stored by the general and null-aware kernels when bound)
     if (g & G_WILLR) m |= 1u << 19;
     if (g & G_MIDPRICE) m |= 1u << 20;
     if (g & G_MIDPOINT) m |= 1u << 21;
@@ -1052,6 +1053,8 @@ static int launch_suite(pqb_panel *p, const Built &full, int64_t b0, int64_t nb,
 #endif
         bool fulls = a.gmask == G_ALL;                                       // exactly the benchmark suite
         for (int k = 0; k < PQB_N_SUITE_OUTPUTS; ++k) fulls &= a.out[k] != nullptr;
+        const bool fastk = a.out[PQB_OUT_FASTK] != nullptr;                  // only the general / null-aware kernels store it
+        fulls &= !fastk;
         // tail spreading: a FEW blocks beyond one CTA per SM (config 2: 157 blocks, 148 SMs) run as 7 single-role CTAs
         // each, which the block scheduler spreads over the SMs instead of doubling the load of a few of them
         // (0.838 -> 0.798 ms at config 2).  Only while every SM still holds at most two CTAs: each single-role CTA has
@@ -1084,7 +1087,7 @@ static int launch_suite(pqb_panel *p, const Built &full, int64_t b0, int64_t nb,
         else if (small)
             suite_fused_kernel<true, false, false, true><<<grid, CTA_THREADS_X, a.smem_bytes, e->stream>>>(a);
         else if (fulls) suite_fused_kernel<true, false><<<grid, CTA_THREADS, a.smem_bytes, e->stream>>>(a);
-        else if (!(a.gmask & ~(unsigned)G_ALL)) {
+        else if (!(a.gmask & ~(unsigned)G_ALL) && !fastk) {
             deal_base_slots(a);
             suite_fused_kernel<false, false, true><<<grid, CTA_THREADS, a.smem_bytes, e->stream>>>(a);
         }
@@ -1218,7 +1221,7 @@ static int launch_suite(pqb_panel *p, const Built &full, int64_t b0, int64_t nb,
 
 // the optional groups report validity per bar: allocate their validity-word planes on first use
 static int ensure_extra_masks(pqb_panel *p, const pqb_suite_params *sp) {
-    if (!(sp->indicators & PQB_IND_EXTRAS)) return PQB_OK;
+    if (!(sp->indicators & PQB_IND_EXTRAS) && !p->d_out[PQB_OUT_FASTK]) return PQB_OK;
     const size_t mwords = (size_t)p->n_blocks * p->bars_padded;
     for (int k = PQB_N_SUITE_OUTPUTS; k < PQB_N_OUTPUTS; ++k)
         if (p->d_out[k] && !p->d_ovm[k]) CU(cudaMalloc(&p->d_ovm[k], mwords * sizeof(uint32_t)));
@@ -1944,5 +1947,6 @@ extern "C" int pqb_multi_run_host(pqb_multi *m, const pqb_suite_params *params) 
 #include "split_host.inc"
 #include "longrows_host.inc"
 #include "windows_host.inc"
+#include "shims_host.inc"
 #include "signals_host.inc"
 #include "info_host.inc"

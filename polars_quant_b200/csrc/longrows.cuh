@@ -45,8 +45,10 @@ struct LongArgs {
     int macd_f, macd_s, macd_g;
     double alpha_g, A_g, Cf, Cs;       // signal chain: alpha, (1 - alpha_g)^L, start-state couplings (see lr_carry_kernel)
     double *seed;                      // [n_ch][n_blocks * 32]
-    double *agg;                       // [n_tiles][n_ch + 1][n_blocks * 32]: B_k, then (in place) the carried end states
+    double *agg;                       // [n_tiles][n_ch + 1][n_blocks * 32]: the tiles' local end states B_k
+    double *carry;                     // same shape: the carried end states y_k
     int n_symbols, n_bars, n_blocks, bars_padded, L, n_tiles;
+    int max_p;                         // the longest period: tiles starting at or after it are past every seed bar
 };
 
 __device__ __forceinline__ double ld_stream(const double *p) { return __ldcs(p); }
@@ -77,6 +79,32 @@ struct MacdHead {
 };
 
 // ---- local: the end state of every chain over one tile from a zero start ---------------------------------------------------
+// Interior tiles (every chain past its seed, a whole tile) take a straight-line path with a compile-time chain count:
+// y = fma(1 - alpha, y, alpha * x) -- one dependent operation per bar and chain; its rounding differs from the
+// reference's fma(alpha, x - y, y) only in the last place of a state that is re-rounded by the carry anyway.  Tile 0, the
+// tiles holding a seed bar and the ragged last tile take the general path.
+template <int NCH, bool MACD>
+__device__ __forceinline__ void lr_local_fast(const LongArgs &A, const double *x, double *out, size_t lanes) {
+    double y[NCH], a1[NCH], al[NCH], g = 0.0;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) { y[c] = 0.0; al[c] = A.alpha[c]; a1[c] = 1.0 - A.alpha[c]; }
+    const double ag = A.alpha_g, ag1 = 1.0 - A.alpha_g;
+    for (int tb = 0; tb < A.L; tb += LR_BATCH) {
+        double xv[LR_BATCH];
+#pragma unroll
+        for (int i = 0; i < LR_BATCH; ++i) xv[i] = ld_stream(x + (size_t)(tb + i) * SYM);
+#pragma unroll
+        for (int i = 0; i < LR_BATCH; ++i) {
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) y[c] = fma(a1[c], y[c], al[c] * xv[i]);
+            if (MACD) g = fma(ag1, g, ag * (y[0] - y[1]));
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) out[(size_t)c * lanes] = y[c];
+    out[(size_t)NCH * lanes] = g;
+}
+
 template <bool MACD>
 __global__ void __launch_bounds__(128) lr_local_kernel(const __grid_constant__ LongArgs A) {
     const int lane = threadIdx.x & 31;
@@ -87,6 +115,17 @@ __global__ void __launch_bounds__(128) lr_local_kernel(const __grid_constant__ L
     const double *x = A.x + ((size_t)b * A.bars_padded + t0) * SYM + lane;
     const size_t lanes = (size_t)A.n_blocks * SYM;
     double *out = A.agg + (size_t)tt * (A.n_ch + 1) * lanes + b * SYM + lane;
+    if (tt > 0 && t0 >= A.max_p && t1 - t0 == A.L) {           // interior tile: every chain runs over the whole tile
+        switch (A.n_ch) {
+            case 1: lr_local_fast<1, MACD>(A, x, out, lanes); return;
+            case 2: lr_local_fast<2, MACD>(A, x, out, lanes); return;
+            case 3: lr_local_fast<3, MACD>(A, x, out, lanes); return;
+            case 4: lr_local_fast<4, MACD>(A, x, out, lanes); return;
+            case 5: lr_local_fast<5, MACD>(A, x, out, lanes); return;
+            case 6: lr_local_fast<6, MACD>(A, x, out, lanes); return;
+            default: break;
+        }
+    }
     double y[LR_MAX_CH];
     int from[LR_MAX_CH];                   // first bar of the tile at which chain c runs its recurrence
 #pragma unroll
@@ -131,51 +170,66 @@ __global__ void __launch_bounds__(128) lr_local_kernel(const __grid_constant__ L
     out[(size_t)A.n_ch * lanes] = g;
 }
 
-// ---- carry: one thread per symbol, serial over the tiles ------------------------------------------------------------------------
-// The loop-carried work is one fma per chain and tile; what would dominate is the latency of the loads of B_k, so they are
-// issued CB tiles ahead (independent of the chain), then consumed in order.
-constexpr int LR_CB = 8;
+// ---- carry: one thread per (symbol, chain), serial over the tiles ------------------------------------------------------------
+// grid.y = chain (n_ch = the MACD signal line).  The loop-carried work is one fma per tile; the loads of B_k are issued
+// LR_CB tiles ahead.  Results go to a second array (`carry`): the signal line's thread re-derives the fast / slow states
+// it needs from the same B_k values the chain threads read.
+constexpr int LR_CB = 16;
 __global__ void __launch_bounds__(64) lr_carry_kernel(const __grid_constant__ LongArgs A) {
     const size_t lanes = (size_t)A.n_blocks * SYM;
     const size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int c = blockIdx.y;
     if (s >= lanes) return;
-    double y[LR_MAX_CH], g = 0.0;
-    int seed_tile[LR_MAX_CH];
-#pragma unroll
-    for (int c = 0; c < LR_MAX_CH; ++c) { y[c] = 0.0; seed_tile[c] = (c < A.n_ch) ? (A.p[c] - 1) / A.L : 0; }
-    const bool macd = A.macd != 0;
     const size_t stride = (size_t)(A.n_ch + 1) * lanes;
-    for (int tb = 0; tb < A.n_tiles; tb += LR_CB) {
-        double bk[LR_CB][LR_MAX_CH + 1];
+    if (c < A.n_ch) {
+        const int seed_tile = (A.p[c] - 1) / A.L;
+        const double Ac = A.A[c];
+        const double *in = A.agg + (size_t)c * lanes + s;
+        double *out = A.carry + (size_t)c * lanes + s;
+        double y = 0.0;
+        for (int tb = 0; tb < A.n_tiles; tb += LR_CB) {
+            double bk[LR_CB];
 #pragma unroll
-        for (int i = 0; i < LR_CB; ++i)
+            for (int i = 0; i < LR_CB; ++i) bk[i] = (tb + i < A.n_tiles) ? __ldcg(in + (size_t)(tb + i) * stride) : 0.0;
 #pragma unroll
-            for (int c = 0; c <= LR_MAX_CH; ++c) {
-                const bool use = (tb + i < A.n_tiles) && (c < A.n_ch || (c == LR_MAX_CH && macd));
-                const int slot = (c == LR_MAX_CH) ? A.n_ch : c;
-                bk[i][c] = use ? __ldcg(A.agg + (size_t)(tb + i) * stride + (size_t)slot * lanes + s) : 0.0;
+            for (int i = 0; i < LR_CB; ++i) {
+                const int tt = tb + i;
+                if (tt >= A.n_tiles) break;
+                if (tt < seed_tile) y = 0.0;
+                else if (tt == seed_tile) y = bk[i];                         // the tile that holds the seed bar starts from the seed
+                else y = fma(Ac, y, bk[i]);
+                out[(size_t)tt * stride] = y;
             }
+        }
+        return;
+    }
+    if (!A.macd) return;
+    // the signal line: it needs the fast / slow states at the START of each tile.  With f_j = f_loc_j + af^(j+1) f0 (and the
+    // same for s), dif_j = dif_loc_j + af^(j+1) f0 - as^(j+1) s0, and the signal's end state is linear in its inputs:
+    // g_end = Ag g0 + g_loc_end + Cf f0 - Cs s0, Cf = alpha_g * sum_j (1 - alpha_g)^(L-1-j) af^(j+1)
+    const double *inf_ = A.agg + s, *ins = A.agg + lanes + s, *ing = A.agg + (size_t)A.n_ch * lanes + s;
+    double *out = A.carry + (size_t)A.n_ch * lanes + s;
+    double f = 0.0, sl = 0.0, g = 0.0;
+    for (int tb = 0; tb < A.n_tiles; tb += LR_CB) {
+        double bf[LR_CB], bs[LR_CB], bg[LR_CB];
+#pragma unroll
+        for (int i = 0; i < LR_CB; ++i) {
+            const bool use = tb + i < A.n_tiles;
+            bf[i] = use ? __ldcg(inf_ + (size_t)(tb + i) * stride) : 0.0;
+            bs[i] = use ? __ldcg(ins + (size_t)(tb + i) * stride) : 0.0;
+            bg[i] = use ? __ldcg(ing + (size_t)(tb + i) * stride) : 0.0;
+        }
 #pragma unroll
         for (int i = 0; i < LR_CB; ++i) {
             const int tt = tb + i;
             if (tt >= A.n_tiles) break;
-            double *rec = A.agg + (size_t)tt * stride + s;
-            // the signal line first: it needs the fast / slow states at the START of this tile.  With f_j = f_loc_j +
-            // af^(j+1) f0 (and the same for s), dif_j = dif_loc_j + af^(j+1) f0 - as^(j+1) s0, and the signal's end state is
-            // linear in its inputs: g_end = Ag g0 + g_loc_end + Cf f0 - Cs s0, Cf = alpha_g * sum_j (1 - alpha_g)^(L-1-j) af^(j+1)
-            if (macd) {
-                if (tt == 0) g = bk[i][LR_MAX_CH];
-                else g = fma(A.A_g, g, bk[i][LR_MAX_CH]) + (A.Cf * y[0] - A.Cs * y[1]);
-                rec[(size_t)A.n_ch * lanes] = g;
+            if (tt == 0) { g = bg[i]; f = bf[i]; sl = bs[i]; }               // (MACD periods fit tile 0: its end states are absolute)
+            else {
+                g = fma(A.A_g, g, bg[i]) + (A.Cf * f - A.Cs * sl);
+                f = fma(A.A[0], f, bf[i]);
+                sl = fma(A.A[1], sl, bs[i]);
             }
-#pragma unroll
-            for (int c = 0; c < LR_MAX_CH; ++c) {
-                if (c >= A.n_ch) continue;
-                if (tt < seed_tile[c]) y[c] = 0.0;
-                else if (tt == seed_tile[c]) y[c] = bk[i][c];                // the tile that holds the seed bar starts from the seed
-                else y[c] = fma(A.A[c], y[c], bk[i][c]);
-                rec[(size_t)c * lanes] = y[c];
-            }
+            out[(size_t)tt * stride] = g;
         }
     }
 }
@@ -191,7 +245,7 @@ __global__ void __launch_bounds__(128) lr_final_kernel(const __grid_constant__ L
     const size_t base = ((size_t)b * A.bars_padded + t0) * SYM + lane;
     const double *x = A.x + base;
     const size_t lanes = (size_t)A.n_blocks * SYM;
-    const double *prev = A.agg + (size_t)(tt > 0 ? tt - 1 : 0) * (A.n_ch + 1) * lanes + b * SYM + lane;
+    const double *prev = A.carry + (size_t)(tt > 0 ? tt - 1 : 0) * (A.n_ch + 1) * lanes + b * SYM + lane;
     double y[LR_MAX_CH];
     int from[LR_MAX_CH];                   // first bar of the tile at which chain c runs its recurrence; its first value is at from - 1
 #pragma unroll

@@ -336,8 +336,8 @@ struct Spec {
     const char *name;
     int n_cols;
     int n_params;
-    const char *pname[3];
-    double pdef[3];
+    const char *pname[6];
+    double pdef[6];
     int n_out;                        // 1 = Float64, >1 = struct
     const char *struct_name;
     const char *out_names[3];
@@ -345,7 +345,7 @@ struct Spec {
 
 enum Fn { F_SMA, F_EMA, F_TEMA, F_TRIMA, F_MA, F_BBANDS, F_MIDPOINT, F_MIDPRICE, F_RSI, F_MACD, F_WILLR, F_MOM,
           F_ROC, F_ROCP, F_ROCR, F_ROCR100, F_CMO, F_MFI, F_CCI, F_TRANGE, F_ATR, F_NATR, F_OBV, F_AD, F_ADOSC,
-          F_STOCH, F_KDJ, F_ADX, F_ADXR, F_DX, F_PLUS_DI, F_MINUS_DI, F_PLUS_DM, F_MINUS_DM, F_TRIX, F_ULTOSC, F_AROON, F_COUNT };
+          F_STOCH, F_KDJ, F_STOCHF, F_STOCHRSI, F_MACDEXT, F_ADX, F_ADXR, F_DX, F_PLUS_DI, F_MINUS_DI, F_PLUS_DM, F_MINUS_DM, F_TRIX, F_ULTOSC, F_AROON, F_COUNT };
 
 const Spec SPECS[F_COUNT] = {
     {"sma", 1, 1, {"timeperiod"}, {30}, 1, nullptr, {}},
@@ -373,8 +373,11 @@ const Spec SPECS[F_COUNT] = {
     {"obv", 2, 0, {}, {}, 1, nullptr, {}},
     {"ad", 4, 0, {}, {}, 1, nullptr, {}},
     {"adosc", 4, 2, {"fastperiod", "slowperiod"}, {3, 10}, 1, nullptr, {}},
-    {"stoch", 3, 3, {"fastk_period", "slowk_period", "slowd_period"}, {5, 3, 3}, 2, "stoch", {"slowk", "slowd"}},
+    {"stoch", 3, 5, {"fastk_period", "slowk_period", "slowk_matype", "slowd_period", "slowd_matype"}, {5, 3, 0, 3, 0}, 2, "stoch", {"slowk", "slowd"}},
     {"kdj", 3, 3, {"fastk_period", "k_period", "d_period"}, {9, 3, 3}, 3, "kdj", {"k", "d", "j"}},
+    {"stochf", 3, 3, {"fastk_period", "fastd_period", "fastd_matype"}, {5, 3, 0}, 2, "stochf", {"fastk", "fastd"}},
+    {"stochrsi", 1, 4, {"timeperiod", "fastk_period", "fastd_period", "fastd_matype"}, {14, 5, 3, 0}, 2, "stochrsi", {"fastk_rsi", "fastd_rsi"}},
+    {"macdext", 1, 6, {"fastperiod", "fastmatype", "slowperiod", "slowmatype", "signalperiod", "signalmatype"}, {12, 0, 26, 0, 9, 0}, 3, "macdext", {"macd_dif", "macd_dea", "macd_hist"}},
     {"adx", 3, 1, {"timeperiod"}, {14}, 1, nullptr, {}},
     {"adxr", 3, 1, {"timeperiod"}, {14}, 1, nullptr, {}},
     {"dx", 3, 1, {"timeperiod"}, {14}, 1, nullptr, {}},
@@ -388,7 +391,7 @@ const Spec SPECS[F_COUNT] = {
 };
 
 int run_fn(int fn, pqb_engine *e, const pqb_col *c, const double *pv, pqb_out_col *o) {
-    const int32_t p0 = (int32_t)pv[0], p1 = (int32_t)pv[1], p2 = (int32_t)pv[2];
+    const int32_t p0 = (int32_t)pv[0], p1 = (int32_t)pv[1], p2 = (int32_t)pv[2], p3 = (int32_t)pv[3], p4 = (int32_t)pv[4], p5 = (int32_t)pv[5];
     switch (fn) {
         case F_SMA: return pqb_sma(e, &c[0], p0, &o[0]);
         case F_EMA: return pqb_ema(e, &c[0], p0, &o[0]);
@@ -415,7 +418,10 @@ int run_fn(int fn, pqb_engine *e, const pqb_col *c, const double *pv, pqb_out_co
         case F_OBV: return pqb_obv(e, &c[0], &c[1], &o[0]);
         case F_AD: return pqb_ad(e, &c[0], &c[1], &c[2], &c[3], &o[0]);
         case F_ADOSC: return pqb_adosc(e, &c[0], &c[1], &c[2], &c[3], p0, p1, &o[0]);
-        case F_STOCH: return pqb_stoch(e, &c[0], &c[1], &c[2], p0, p1, p2, &o[0], &o[1]);
+        case F_STOCH: return pqb_stoch_ma(e, &c[0], &c[1], &c[2], p0, p1, p2, p3, p4, &o[0], &o[1]);
+        case F_STOCHF: return pqb_stochf(e, &c[0], &c[1], &c[2], p0, p1, p2, &o[0], &o[1]);
+        case F_STOCHRSI: return pqb_stochrsi(e, &c[0], p0, p1, p2, p3, &o[0], &o[1]);
+        case F_MACDEXT: return pqb_macdext(e, &c[0], p0, p1, p2, p3, p4, p5, &o[0], &o[1], &o[2]);
         case F_KDJ: return pqb_kdj(e, &c[0], &c[1], &c[2], p0, p1, p2, &o[0], &o[1], &o[2]);
         // the directional-movement family: one fused call, one requested output (momentum.rs:11-61, 226-237, 344-436)
         case F_ADX: return pqb_dm(e, &c[0], &c[1], &c[2], p0, nullptr, nullptr, nullptr, nullptr, &o[0], nullptr);
@@ -437,7 +443,7 @@ bool call_impl(int fn, pqb_series_export *in, size_t n_in, const uint8_t *kw, si
     if (!in || n_in < (size_t)S.n_cols) { set_err("%s: expected %d input columns, got %zu", S.name, S.n_cols, n_in); return false; }
     if (!ret) { set_err("%s: NULL return_value", S.name); return false; }
     // parameters: defaults <- trailing literal inputs (the Python shims) <- pickled kwargs (the Rust structs)
-    double pv[3] = {S.pdef[0], S.pdef[1], S.pdef[2]};
+    double pv[6] = {S.pdef[0], S.pdef[1], S.pdef[2], S.pdef[3], S.pdef[4], S.pdef[5]};
     for (int k = 0; k < S.n_params; ++k)
         if ((size_t)(S.n_cols + k) < n_in) {
             double v;
@@ -706,6 +712,9 @@ PQB_DEFINE_PLUGIN(ad, F_AD)
 PQB_DEFINE_PLUGIN(adosc, F_ADOSC)
 PQB_DEFINE_PLUGIN(stoch, F_STOCH)
 PQB_DEFINE_PLUGIN(kdj, F_KDJ)
+PQB_DEFINE_PLUGIN(stochf, F_STOCHF)
+PQB_DEFINE_PLUGIN(stochrsi, F_STOCHRSI)
+PQB_DEFINE_PLUGIN(macdext, F_MACDEXT)
 PQB_DEFINE_PLUGIN(adx, F_ADX)
 PQB_DEFINE_PLUGIN(adxr, F_ADXR)
 PQB_DEFINE_PLUGIN(dx, F_DX)

@@ -19,10 +19,10 @@
 
 namespace pqb {
 
-constexpr int W_MAX_UNITS = 4;        // role warps per CTA (+ 1 producer warp)
+constexpr int W_MAX_UNITS = 5;        // role warps per CTA (+ 1 producer warp)
 constexpr int W_MAX_GROUPS = 4;
 constexpr int W_THREADS = 32 * (W_MAX_UNITS + 1);
-constexpr int W_SMEM_MAX = 64;        // windows up to this many bars keep their van Herk arrays in shared memory
+constexpr int W_SMEM_MAX = 32;        // windows up to this many bars keep their van Herk arrays in shared memory (PQB_WIN_SMEM_MAX)
 constexpr int W_FIELDS = 3;           // close, high, low
 constexpr int W_STAGE_BYTES = W_FIELDS * SB * SYM * 8;      // 6 KB
 

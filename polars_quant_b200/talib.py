@@ -198,12 +198,28 @@ def AROON(high, low, timeperiod: int = 14):
 
 def STOCH(high, low, close, fastk_period: int = 5, slowk_period: int = 3, slowk_matype: int = 0,
           slowd_period: int = 3, slowd_matype: int = 0):
-    """STOCH - Stochastic (SlowK, SlowD).  The reference composes it in Python from polars rolling
-    min / max and two MA plugin calls (momentum.py:178-186); here it is one fused call.  Only matype 0
-    (SMA) smoothings are built."""
-    if slowk_matype != 0 or slowd_matype != 0:
-        raise NotImplementedError("STOCH smoothing matype != 0 is not built (SURVEY.md 8a)")
-    return _call("stoch", [high, low, close], [fastk_period, slowk_period, slowd_period], ("slowk", "slowd"))
+    """STOCH - Stochastic (SlowK, SlowD).  The reference composes it in Python from polars rolling min / max and two
+    MA plugin calls (momentum.py:178-186); here it is one call (fused kernel for SMA smoothings, a chain of device
+    passes for the other matypes)."""
+    return _call("stoch", [high, low, close], [fastk_period, slowk_period, slowk_matype, slowd_period, slowd_matype],
+                 ("slowk", "slowd"))
+
+
+def STOCHF(high, low, close, fastk_period: int = 5, fastd_period: int = 3, fastd_matype: int = 0):
+    """STOCHF - Stochastic Fast (FastK, FastD) (momentum.py:188-195)"""
+    return _call("stochf", [high, low, close], [fastk_period, fastd_period, fastd_matype], ("fastk", "fastd"))
+
+
+def STOCHRSI(real, timeperiod: int = 14, fastk_period: int = 5, fastd_period: int = 3, fastd_matype: int = 0):
+    """STOCHRSI - Stochastic Relative Strength Index (FastK, FastD) (momentum.py:197-205)"""
+    return _call("stochrsi", [real], [timeperiod, fastk_period, fastd_period, fastd_matype], ("fastk_rsi", "fastd_rsi"))
+
+
+def MACDEXT(real, fastperiod: int = 12, fastmatype: int = 0, slowperiod: int = 26, slowmatype: int = 0,
+            signalperiod: int = 9, signalmatype: int = 0):
+    """MACDEXT - MACD with controllable MA type (macd_dif, macd_dea, macd_hist) (momentum.py:83-88)"""
+    return _call("macdext", [real], [fastperiod, fastmatype, slowperiod, slowmatype, signalperiod, signalmatype],
+                 ("macd_dif", "macd_dea", "macd_hist"))
 
 
 def KDJ(high, low, close, fastk_period: int = 9, k_period: int = 3, d_period: int = 3):
@@ -244,6 +260,6 @@ def ADOSC(high, low, close, volume, fastperiod: int = 3, slowperiod: int = 10):
 
 
 __all__ = ["SMA", "EMA", "TEMA", "TRIMA", "MA", "BBANDS", "MIDPOINT", "MIDPRICE", "RSI", "MACD", "MACDFIX", "WILLR",
-           "MOM", "ROC", "ROCP", "ROCR", "ROCR100", "CMO", "MFI", "CCI", "STOCH", "KDJ", "TRANGE", "ATR", "NATR",
+           "MOM", "ROC", "ROCP", "ROCR", "ROCR100", "CMO", "MFI", "CCI", "STOCH", "STOCHF", "STOCHRSI", "MACDEXT", "KDJ", "TRANGE", "ATR", "NATR",
            "OBV", "AD", "ADOSC", "ADX", "ADXR", "DX", "PLUS_DI", "MINUS_DI", "PLUS_DM", "MINUS_DM", "TRIX", "ULTOSC",
            "AROON"]

@@ -58,8 +58,6 @@ def gpu_call(entry, cols):
     a = lambda name: _arrow(cols, name, entry)
     if entry["kind"] == "py":
         if fn == "STOCH":
-            if pr[2] != 0 or pr[4] != 0:
-                return None
             return list(T.STOCH(a("high"), a("low"), a("close"), *pr))
         if fn == "MACDFIX":
             return list(T.MACDFIX(a("close"), *pr))
@@ -159,5 +157,4 @@ def test_gpu_reproduces_the_executed_reference(tag):
         done["bit_exact"] += 1
     print(tag, dict(done))
     assert done["bit_exact"] + done["fails_alike"] >= 60, done
-    # the only golden calls without a product entry point: STOCH with a non-SMA smoothing (matype != 0)
-    assert all(k.startswith("STOCH_14_5_1") for k in missing), missing
+    assert not missing, missing                        # every golden call has a product entry point
