@@ -171,6 +171,7 @@ def lib() -> C.CDLL:
         L.pqb_suite_params_default.argtypes = [C.POINTER(SuiteParams)]
         L.pqb_suite_params_default.restype = None
         L.pqb_signals_run.argtypes = [C.c_void_p, C.c_double, C.c_double]
+        L.pqb_ma_cross_run.argtypes = [C.c_void_p, C.c_int, C.c_int32, C.c_int32]
         L.pqb_panel_host_signal.argtypes = [C.c_void_p, C.c_int]
         L.pqb_panel_host_signal.restype = C.c_void_p
         L.pqb_panel_device_signal.argtypes = [C.c_void_p, C.c_int]

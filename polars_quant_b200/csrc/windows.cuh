@@ -52,6 +52,28 @@ struct WinArgs {
 };
 
 // van Herk / Gil-Werman in an L2-resident global scratch: same algorithm as Ext (suite_kernel.cuh), rows of 32 lanes.
+// Block end (once per p bars): raw values -> suffix extremes in place, newest to oldest; loads batched 8 ahead of the max
+// chain.  Out of line: the steady loop keeps only the per-bar work (and its registers).
+__device__ __noinline__ void extg_rebuild(double *hb, double *lb, int p) {
+    double sh = ninf(), sl = pinf();
+    int q = p;
+    while (q > 0) {
+        const int nb = min(q, 8);
+        double a[8], b[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            if (i < nb) { a[i] = __ldcg(hb + (q - 1 - i) * SYM); b[i] = __ldcg(lb + (q - 1 - i) * SYM); }
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            if (i < nb) {
+                sh = dmax(sh, a[i]);
+                sl = dmin(sl, b[i]);
+                __stcg(hb + (q - 1 - i) * SYM, sh);
+                __stcg(lb + (q - 1 - i) * SYM, sl);
+            }
+        q -= nb;
+    }
+}
 struct ExtG {
     double *hb, *lb;
     int off, p;
@@ -64,8 +86,8 @@ struct ExtG {
         ph = ninf();
         pl = pinf();
         for (int q = 0; q <= p; ++q) {
-            __stcg(hb + (size_t)q * SYM, ninf());
-            __stcg(lb + (size_t)q * SYM, pinf());
+            __stcg(hb + q * SYM, ninf());
+            __stcg(lb + q * SYM, pinf());
         }
         nh = ninf();
         nl = pinf();
@@ -75,45 +97,24 @@ struct ExtG {
         pl = dmin(pl, l);
         hn = dmax(ph, nh);
         ln = dmin(pl, nl);
-        __stcg(hb + (size_t)off * SYM, h);
-        __stcg(lb + (size_t)off * SYM, l);
+        __stcg(hb + off * SYM, h);
+        __stcg(lb + off * SYM, l);
         ++off;
         if (off == p) {
-            // block end: raw values -> suffix extremes in place, newest to oldest; loads batched 8 ahead of the max chain
-            double sh = ninf(), sl = pinf();
-            int q = p;
-            while (q > 0) {
-                const int nb = min(q, 8);
-                double a[8], b[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i)
-                    if (i < nb) { a[i] = __ldcg(hb + (size_t)(q - 1 - i) * SYM); b[i] = __ldcg(lb + (size_t)(q - 1 - i) * SYM); }
-#pragma unroll
-                for (int i = 0; i < 8; ++i)
-                    if (i < nb) {
-                        sh = dmax(sh, a[i]);
-                        sl = dmin(sl, b[i]);
-                        __stcg(hb + (size_t)(q - 1 - i) * SYM, sh);
-                        __stcg(lb + (size_t)(q - 1 - i) * SYM, sl);
-                    }
-                q -= nb;
-            }
+            extg_rebuild(hb, lb, p);
             ph = ninf();
             pl = pinf();
             off = 0;
         }
         // the suffix extremes the NEXT bar needs (slot off + 1; slot p is the sentinel): issued now, consumed a bar later
-        nh = __ldcg(hb + (size_t)(off + 1) * SYM);
-        nl = __ldcg(lb + (size_t)(off + 1) * SYM);
+        nh = __ldcg(hb + (off + 1) * SYM);
+        nl = __ldcg(lb + (off + 1) * SYM);
     }
 };
 
 struct WCtx {
-    const WinArgs &A;
-    const WinUnit &U;
-    double *smem;      // ring area
     size_t pos;        // element offset of (this lane, current bar)
-    int lane, a;
+    int a, n_bars;     // this lane's first valid bar; bars of the panel
 };
 
 // ---- KDJ(k, sk, sd) ---------------------------------------------------------------------------------------------------------
@@ -122,11 +123,15 @@ struct UnitKdj {
     EXT ek;
     Ring fr, sr;
     double s_k, s_d;
+    struct { int w, sk, sd; double inv_sk, inv_sd; double *out[3]; } U;      // this unit's parameters, in registers
+    __device__ __forceinline__ void take(const WinUnit &u) {
+        U.w = u.w; U.sk = u.sk; U.sd = u.sd; U.inv_sk = u.inv_sk; U.inv_sd = u.inv_sd;
+        U.out[0] = u.out[0]; U.out[1] = u.out[1]; U.out[2] = u.out[2];
+    }
     template <bool STEADY>
     __device__ __forceinline__ void step(const WCtx &X, int t, double c, double h, double l) {
-        const WinUnit &U = X.U;
         const int j = t - X.a;
-        const bool live = STEADY || t < X.A.n_bars;
+        const bool live = STEADY || t < X.n_bars;
         const bool in = STEADY || (j >= 0 && live);
         const double nn = qnan();
         double hn, ln;
@@ -166,11 +171,15 @@ struct UnitKdj {
 template <class EXT>
 struct UnitWmd {
     EXT ew;
+    struct { int w; double *out[4]; } U;
+    __device__ __forceinline__ void take(const WinUnit &u) {
+        U.w = u.w;
+        for (int q = 0; q < 4; ++q) U.out[q] = u.out[q];
+    }
     template <bool STEADY>
     __device__ __forceinline__ void step(const WCtx &X, int t, double c, double h, double l) {
-        const WinUnit &U = X.U;
         const int j = t - X.a;
-        const bool live = STEADY || t < X.A.n_bars;
+        const bool live = STEADY || t < X.n_bars;
         const bool in = STEADY || (j >= 0 && live);
         const double nn = qnan();
         double hn, ln;
@@ -195,11 +204,12 @@ struct UnitWmd {
 struct UnitAtr {
     Ema atr;
     double pc;
+    struct { int ep; double alpha; double *out[1]; } U;
+    __device__ __forceinline__ void take(const WinUnit &u) { U.ep = u.ep; U.alpha = u.alpha; U.out[0] = u.out[0]; }
     template <bool STEADY>
     __device__ __forceinline__ void step(const WCtx &X, int t, double c, double h, double l) {
-        const WinUnit &U = X.U;
         const int j = t - X.a;
-        const bool live = STEADY || t < X.A.n_bars;
+        const bool live = STEADY || t < X.n_bars;
         const double tr = rs_max(rs_max(h - l, fabs(h - pc)), fabs(l - pc));             // volatility.rs:77
         const bool ok = atr.step<STEADY>(tr, j - 1, U.ep, U.alpha);                      // :30 calc_ema(trange, 2p-1)
         stg(U.out[0] + X.pos, (ok && live) ? atr.y : qnan());
@@ -208,12 +218,13 @@ struct UnitAtr {
 };
 
 template <class UNIT>
-__device__ __forceinline__ void run_unit(UNIT &R, const WinArgs &A, const WinUnit &U, uint32_t full, uint32_t empty,
+__device__ __forceinline__ void run_unit(UNIT &R, const WinArgs &A, const WinUnit &U_, uint32_t full, uint32_t empty,
                                          double *ring_smem, int block, int lane) {
+    R.take(U_);
     const int sym = block * SYM + lane;
     const int a = A.start ? A.start[(sym < A.n_symbols) ? sym : block * SYM] : 0;
     const int src_lane = (sym < A.n_symbols) ? lane : 0;   // lanes past the last symbol follow lane 0 (no slow-path divisions)
-    WCtx X{A, U, ring_smem, (size_t)block * A.bars_padded * SYM + lane, lane, a};
+    WCtx X{(size_t)block * A.bars_padded * SYM + lane, a, A.n_bars};
     int amax = a;
 #pragma unroll
     for (int d = 16; d >= 1; d >>= 1) amax = max(amax, __shfl_xor_sync(FULL, amax, d));
@@ -253,7 +264,8 @@ __global__ void __launch_bounds__(W_THREADS, 3) window_suite_kernel(const __grid
     double *rings = reinterpret_cast<double *>(empty_p + NS);
     const uint32_t stage = smem_u32(smem_dyn), full = smem_u32(full_p), empty = smem_u32(empty_p);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int g = (int)(blockIdx.x % (unsigned)A.n_groups), block = (int)(blockIdx.x / (unsigned)A.n_groups);
+    // group-major: the CTAs of the heaviest group (group 0) are scheduled first, the lighter groups fill in behind them
+    const int g = (int)(blockIdx.x / (unsigned)A.n_blocks), block = (int)(blockIdx.x % (unsigned)A.n_blocks);
     const int n_units = A.n_units[g];
     if (threadIdx.x == 0) {
 #pragma unroll

@@ -249,6 +249,18 @@ class Panel:
             res[name] = self._view(ptr, C.c_int8, self.n_symbols * self.pitch, np.int8).reshape(self.n_symbols, self.pitch)[:, :self.n_bars]
         return res
 
+    def ma_cross(self, fast_period: int = 10, slow_period: int = 20, ma_type: str = "sma"):
+        """MA golden / death cross (README.md:876-905 `Strategy.ma`): int8 [n_symbols, n_bars], +1 where MA(close, fast)
+        crosses above MA(close, slow), -1 where it crosses below.  close must be on the device (upload / run_host)."""
+        kinds = {"sma": 0, "ema": 1}
+        if ma_type not in kinds:
+            raise ValueError("ma_type %r: 'sma' and 'ema' are built" % (ma_type,))
+        N.check(N.lib().pqb_ma_cross_run(self._h, kinds[ma_type], fast_period, slow_period))
+        ptr = N.lib().pqb_panel_host_signal(self._h, 3)
+        if not ptr:
+            raise ValueError("signals need a panel with host staging")
+        return self._view(ptr, C.c_int8, self.n_symbols * self.pitch, np.int8).reshape(self.n_symbols, self.pitch)[:, :self.n_bars]
+
     def info(self):
         """Last-row reductions per symbol (the README's `Selector.info()` columns that come from close / high / low /
         volume; include/pqb200.h `pqb_panel_info`): {name: (float64[n_symbols], bool[n_symbols] valid)}.  The inputs

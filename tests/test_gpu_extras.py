@@ -338,3 +338,35 @@ def test_engine_destroyed_before_its_panels_is_deferred():
     assert not T.compare_all(res, out, ok, pqo.OUTPUT_NAMES)
     p.close()
     cp.close()                                             # last one out frees the engine
+
+
+def test_ma_golden_and_death_cross_signal():
+    """README.md:876-905 `Strategy.ma(df, fast_period, slow_period, ma_type)`: cross(MA(close, fast), MA(close, slow)) as int8,
+    both averages computed inside the signal kernel with the suite's serial arithmetic -- compared with the crossing rule
+    evaluated in numpy on the ORACLE's SMA / EMA columns (calc_sma overlap.rs:871, calc_ema :660)."""
+    import polars_quant_b200 as pq
+    S, N = 70, 900
+    d = synth.ohlcv(S, N, seed=99)
+    starts = np.zeros(S, dtype=np.int32)
+    starts[[4, 33, 69]] = (25, 400, 880)
+    panel = pq.Panel(S, N)
+    panel.set_fields(d["close"], d["high"], d["low"], d["volume"], starts=starts)
+    panel.upload()
+
+    def cross(a, b):
+        out = np.zeros(a.shape, dtype=np.int8)
+        with np.errstate(invalid="ignore"):
+            out[1:][(a[1:] > b[1:]) & (a[:-1] <= b[:-1])] = 1
+            out[1:][(a[1:] < b[1:]) & (a[:-1] >= b[:-1])] = -1
+        return out
+
+    for ma_type, fn, fast, slow in (("sma", pqo.sma, 5, 10), ("sma", pqo.sma, 10, 20), ("ema", pqo.ema, 12, 26), ("sma", pqo.sma, 20, 7)):
+        sig = panel.ma_cross(fast, slow, ma_type).copy()
+        assert set(np.unique(sig).tolist()) <= {-1, 0, 1} and (sig != 0).sum() > 1000
+        for s in (0, 4, 33, 50, 69):
+            a = int(starts[s])
+            f, g = fn(d["close"][s][a:], fast), fn(d["close"][s][a:], slow)
+            fv = np.full(N, np.nan); gv = np.full(N, np.nan)
+            fv[a:] = np.where(f[1], f[0], np.nan); gv[a:] = np.where(g[1], g[0], np.nan)
+            assert np.array_equal(sig[s], cross(fv, gv)), (ma_type, fast, slow, s)
+    panel.close()

@@ -154,6 +154,38 @@ def test_nan_and_inf_inputs_propagate_like_the_reference(pq):
     panel.close()
 
 
+def test_nan_values_in_high_and_low_willr_follows_f64_max(pq):
+    """willr folds its window with f64::max / f64::min, which ignore a NaN operand (momentum.rs:644-650); the reference
+    is deterministic there and the CUDA path's running extremes follow the same rule -- bit-exact, also through the
+    full-suite kernel where WILLR and MIDPRICE share one pair of van Herk arrays.  (midprice / midpoint keep monotonic
+    deques whose compares are false on NaN, overlap.rs:206-221: while a NaN sits in such a window the reference returns
+    the maximum of the bars BEFORE it -- an artifact of the container the CUDA path does not reproduce: DESIGN.md 5.)"""
+    d = synth.ohlcv(6, 400, seed=78)
+    d["high"][0, 90] = np.nan
+    d["low"][1, 130] = np.nan
+    d["high"][2, 131] = np.nan
+    d["low"][2, 131] = np.nan
+    d["high"][3, 5:25] = np.nan                  # a whole window of NaN highs (p = 14)
+    S, N = d["close"].shape
+    panel = pq.Panel(S, N)
+    panel.set_fields(d["close"], d["high"], d["low"], d["volume"])
+    res = panel.compute()
+    for s in range(S):
+        rv, rk = pqo.willr(d["high"][s], d["low"][s], d["close"][s], 14)
+        nbad, msg = T.compare("willr", res["willr"][0][s], res["willr"][1][s], rv, rk)
+        assert nbad == 0, f"symbol {s}: {msg}"
+    # outside the windows that hold a NaN everything else is untouched
+    out, ok = _oracle(d)
+    clean = np.ones((S, N), bool)
+    for s, t in ((0, 90), (1, 130), (2, 131)):
+        clean[s, t:t + 14] = False
+    clean[3, 5:25 + 14] = False
+    for name in ("midprice",):
+        j = pqo.OUTPUT_NAMES.index(name)
+        assert T.same_bits(res[name][0][clean], out[j][clean]).all(), name
+    panel.close()
+
+
 def test_partial_suites_and_single_indicator_masks(pq):
     """Any subset of indicator groups (the non-specialised kernel): outputs of enabled groups match,
     disabled outputs stay unallocated."""
