@@ -55,7 +55,7 @@ struct WinArgs {
 // Block end (once per p bars): raw values -> suffix extremes in place, newest to oldest; loads batched 8 ahead of the max
 // chain.  Out of line: the steady loop keeps only the per-bar work (and its registers).
 __device__ __noinline__ void extg_rebuild(double *hb, double *lb, int p) {
-    double sh = ninf(), sl = pinf();
+    double sh = vmin(), sl = vmax();
     int q = p;
     while (q > 0) {
         const int nb = min(q, 8);
@@ -83,14 +83,14 @@ struct ExtG {
         lb = l + lane;
         p = p_;
         off = 0;
-        ph = ninf();
-        pl = pinf();
+        ph = vmin();
+        pl = vmax();
         for (int q = 0; q <= p; ++q) {
-            __stcg(hb + q * SYM, ninf());
-            __stcg(lb + q * SYM, pinf());
+            __stcg(hb + q * SYM, vmin());
+            __stcg(lb + q * SYM, vmax());
         }
-        nh = ninf();
-        nl = pinf();
+        nh = vmin();
+        nl = vmax();
     }
     __device__ __forceinline__ void step(double h, double l, double &hn, double &ln) {
         ph = dmax(ph, h);
@@ -102,8 +102,8 @@ struct ExtG {
         ++off;
         if (off == p) {
             extg_rebuild(hb, lb, p);
-            ph = ninf();
-            pl = pinf();
+            ph = vmin();
+            pl = vmax();
             off = 0;
         }
         // the suffix extremes the NEXT bar needs (slot off + 1; slot p is the sentinel): issued now, consumed a bar later
