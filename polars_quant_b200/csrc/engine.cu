@@ -1570,7 +1570,8 @@ static ColCheck scan_col(const pqb_col *c) {
     return r;
 }
 
-enum NullPolicy { NP_SHIFT, NP_ERR };   // overlap/volatility/volume functions skip nulls; momentum.rs errors
+enum NullPolicy { NP_SHIFT, NP_ERR, NP_LEAD };   // overlap/volatility/volume functions skip nulls; momentum.rs errors;
+                                                  // NP_LEAD: a null-skipping function built for leading nulls only
 
 static int run_single(pqb_engine *e, const pqb_col *const *cols, const int *fields, int n_cols, NullPolicy np,
                       const pqb_suite_params *sp, const int *outs, pqb_out_col *const *dst, int n_out) {
@@ -1588,6 +1589,9 @@ static int run_single(pqb_engine *e, const pqb_col *const *cols, const int *fiel
         ColCheck cc = scan_col(cols[i]);
         if (cc.any_null && np == NP_ERR)
             return fail(PQB_ERR_NULLS, "chunked array is not contiguous (input %d has nulls; reference: cont_slice()?)", i);
+        if (cc.interior && np == NP_LEAD)
+            return fail(PQB_ERR_UNSUPPORTED, "input %d has interior / trailing nulls: the reference skips null bars here, this build "
+                                             "handles leading nulls only for this function", i);
     }
     if (n == 0) return PQB_OK;
     // device required from here on
@@ -1765,14 +1769,14 @@ extern "C" int pqb_midprice(pqb_engine *e, const pqb_col *h, const pqb_col *l, i
 extern "C" int pqb_midpoint(pqb_engine *e, const pqb_col *real, int32_t tp, pqb_out_col *out) {
     pqb_suite_params sp = only(PQB_IND_MIDPOINT); sp.midpoint_period = tp;
     const pqb_col *c[] = {real}; const int f[] = {PQB_CLOSE}; const int o[] = {PQB_OUT_MIDPOINT}; pqb_out_col *d[] = {out};
-    return run_single(e, c, f, 1, NP_ERR, &sp, o, d, 1);      // (null-skipping in the reference; not built with nulls yet)
+    return run_single(e, c, f, 1, NP_LEAD, &sp, o, d, 1);     // (null-skipping in the reference; interior nulls not built yet)
 }
 extern "C" int pqb_adosc(pqb_engine *e, const pqb_col *h, const pqb_col *l, const pqb_col *cl, const pqb_col *v,
                          int32_t fp, int32_t slp, pqb_out_col *out) {
     pqb_suite_params sp = only(PQB_IND_ADOSC); sp.adosc_fast = fp; sp.adosc_slow = slp;
     const pqb_col *c[] = {h, l, cl, v}; const int f[] = {PQB_HIGH, PQB_LOW, PQB_CLOSE, PQB_VOLUME};
     const int o[] = {PQB_OUT_ADOSC}; pqb_out_col *d[] = {out};
-    return run_single(e, c, f, 4, NP_ERR, &sp, o, d, 1);
+    return run_single(e, c, f, 4, NP_LEAD, &sp, o, d, 1);     // (calc_ad / calc_ema skip null bars; interior nulls not built yet)
 }
 extern "C" int pqb_mom(pqb_engine *e, const pqb_col *real, int32_t tp, pqb_out_col *out) {
     pqb_suite_params sp = only(PQB_IND_MOM); sp.mom_period = tp;

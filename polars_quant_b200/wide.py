@@ -220,6 +220,7 @@ class WidePanel:
         self._suite = None
         self._candles = None
         self._batch = None
+        self.last_timings = {}
 
     def _col(self, name):
         return self.table.column(self._index[name])
@@ -259,6 +260,16 @@ class WidePanel:
         come back as ONE record batch aliasing the pinned result planes (pqb_panel_export_arrow) -- no per-column work in
         Python.  `devices`: GPU ordinals to shard the symbols over (contiguous ranges, one host thread per GPU, no
         collective -- SURVEY.md 8e); default: this panel's engine only."""
+        import time
+        tm = self.last_timings = {}
+        t_ = time.perf_counter()
+
+        def lap(name):
+            nonlocal t_
+            now = time.perf_counter()
+            tm[name] = tm.get(name, 0.0) + (now - t_) * 1e3
+            t_ = now
+
         symbols, cols = split_columns(self.table, SUITE_FIELDS)
         symbols = [s for s in symbols if all(s in cols[f] for f in SUITE_FIELDS)]
         if not symbols:
@@ -267,7 +278,9 @@ class WidePanel:
         names = list(outputs) if outputs is not None else N.OUTPUT_NAMES[:N.N_SUITE_OUTPUTS]
         omask = sum(1 << N.OUTPUT_NAMES.index(n) for n in names)
         self._suite = None          # (an earlier panel no result refers to any more goes back to the engine's pinned pool first)
+        lap("release_previous_panel_ms")
         sym, fld = self._suite_map(symbols, cols)
+        lap("column_map_ms")
         engines = [self.engine or get_engine(0)] if not devices else [get_engine(d) for d in devices]
         from .shard import symbol_range
         shards = []
@@ -281,17 +294,25 @@ class WidePanel:
         def run(i):
             eng, lo, hi = shards[i]
             try:
+                t0 = time.perf_counter()
                 p = Panel(hi - lo, self.n_bars, engine=eng, outputs_mask=omask)
+                tm["panel_create_ms"] = tm.get("panel_create_ms", 0.0) + (time.perf_counter() - t0) * 1e3
                 mine = (fld >= 0) & (sym >= lo) & (sym < hi)
                 s_i = np.ascontiguousarray(np.where(mine, sym - lo, 0), dtype=np.int64)
                 f_i = np.ascontiguousarray(np.where(mine, fld, -1), dtype=np.int32)
+                t0 = time.perf_counter()
                 arr, sch = self._record_batch()
+                t1 = time.perf_counter()
                 try:
                     N.check(N.lib().pqb_suite_run_record_batch(p._h, C.byref(params), C.byref(arr), C.byref(sch), s_i.ctypes.data,
                                                                f_i.ctypes.data, threads))
                 finally:
                     self._release(arr, sch)
+                t2 = time.perf_counter()
                 batches[i] = (p, p.export_arrow(omask, symbols[lo:hi]))
+                t3 = time.perf_counter()
+                for k, v in (("export_input_batch_ms", t1 - t0), ("run_record_batch_ms", t2 - t1), ("export_results_ms", t3 - t2)):
+                    tm[k] = tm.get(k, 0.0) + v * 1e3
             except Exception as ex:                      # (raised again on the calling thread)
                 errors.append(ex)
 
@@ -306,6 +327,7 @@ class WidePanel:
                 t.join()
         if errors:
             raise errors[0]
+        t_ = time.perf_counter()
         self._suite = [p for p, _ in batches]
         if len(batches) == 1:
             out = pa.Table.from_batches([batches[0][1]])
@@ -317,6 +339,7 @@ class WidePanel:
             out = pa.table(out_cols, names=out_names)
         if self.dates is not None:
             out = out.add_column(0, "date", self.dates)
+        lap("assemble_table_ms")
         return out
 
     # ---- Selector.info(): last-row reductions (README.md:832-851) ----

@@ -45,7 +45,7 @@ def main():
             del out
         rec = {"workload": "WidePanel.suite(): %d symbols x %d bars, %d columns in, %d out" % (S, N, t.num_columns, 21 * S + 1),
                "devices": devices or [0], "first_call_ms": times[0] * 1e3, "ms": min(times[1:]) * 1e3,
-               "symbol_bars_per_s": S * N / min(times[1:])}
+               "symbol_bars_per_s": S * N / min(times[1:]), "last_call_stages_ms": {k: round(v, 2) for k, v in wp.last_timings.items()}}
         if "--cpu" in sys.argv:
             from oracle import pqo
             ns = min(S, 512)
