@@ -77,7 +77,9 @@ __device__ __noinline__ void extg_rebuild(double *hb, double *lb, int p) {
 struct ExtG {
     double *hb, *lb;
     int off, p;
-    double ph, pl, nh, nl;             // running prefix extremes; the previous block's suffix extremes at slot off + 1
+    double ph, pl;                     // running prefix extremes of the current block
+    double nh, nl, nh2, nl2;           // the previous block's suffix extremes at slots off + 1 and off + 2: loaded TWO bars ahead
+                                       // of their use, so that an L2 round trip (~250 cycles + queueing) hides behind two bars of arithmetic
     __device__ __forceinline__ void init(double *h, double *l, int p_, int lane) {
         hb = h + lane;
         lb = l + lane;
@@ -89,8 +91,8 @@ struct ExtG {
             __stcg(hb + q * SYM, vmin());
             __stcg(lb + q * SYM, vmax());
         }
-        nh = vmin();
-        nl = vmax();
+        nh = nh2 = vmin();
+        nl = nl2 = vmax();
     }
     __device__ __forceinline__ void step(double h, double l, double &hn, double &ln) {
         ph = dmax(ph, h);
@@ -105,10 +107,14 @@ struct ExtG {
             ph = vmin();
             pl = vmax();
             off = 0;
+            nh2 = __ldcg(hb + min(1, p) * SYM);              // (slot p is the sentinel)
+            nl2 = __ldcg(lb + min(1, p) * SYM);
         }
-        // the suffix extremes the NEXT bar needs (slot off + 1; slot p is the sentinel): issued now, consumed a bar later
-        nh = __ldcg(hb + (off + 1) * SYM);
-        nl = __ldcg(lb + (off + 1) * SYM);
+        nh = nh2;
+        nl = nl2;
+        const int q = min(off + 2, p);
+        nh2 = __ldcg(hb + q * SYM);
+        nl2 = __ldcg(lb + q * SYM);
     }
 };
 
