@@ -58,6 +58,7 @@ class CandlePanel:
         if not ptr:
             raise ValueError("this plane was not allocated")
         buf = (C.c_char * (self.n_symbols * cols * np.dtype(dtype).itemsize)).from_address(ptr)
+        buf._owner = self                  # the view keeps the panel (and its pinned planes) alive, like Panel._view
         return np.frombuffer(buf, dtype=dtype).reshape(self.n_symbols, cols)
 
     def host_field(self, f: int) -> np.ndarray:

@@ -62,14 +62,21 @@ if big:
                  "algorithmic_bytes_per_launch": 200 * 50000 * 5040, "ncu_ms": e.get("gpu__time_duration.sum"),
                  "captured_at_commit": commit,
                  "source": "profiles/%s (ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum over bench.py --steps 2 --warmup 1 --no-e2e --no-cpu)" % Path(src).name})
-for pat, S, N, B, label in (("window_suite_kernel", 10000, 5040, 248, "c5"), ("lr_local_kernel", 500, 1000000, 64, "c3")):
-    ks = [e for e in launches if pat in e["kernel"]]
-    if ks:
-        e = max(ks, key=lambda e: e.get("gpu__time_duration.sum", 0.0))
-        recs.append({"workload": label, "symbols_": S, "bars_": N, "kernel": short(e["kernel"]), "grid": e["grid"],
-                     "dram_bytes_read": e.get("dram__bytes_read.sum"), "dram_bytes_write": e.get("dram__bytes_write.sum"),
-                     "dram_bytes_per_launch": e.get("dram__bytes_read.sum", 0.0) + e.get("dram__bytes_write.sum", 0.0),
-                     "algorithmic_bytes_per_pass": B * S * N, "ncu_ms": e.get("gpu__time_duration.sum"), "captured_at_commit": commit})
+ks = [e for e in launches if "window_suite_kernel" in e["kernel"]]
+if ks:
+    e = max(ks, key=lambda e: e.get("gpu__time_duration.sum", 0.0))
+    recs.append({"workload": "c5", "symbols_": 10000, "bars_": 5040, "kernel": short(e["kernel"]), "grid": e["grid"],
+                 "dram_bytes_read": e.get("dram__bytes_read.sum"), "dram_bytes_write": e.get("dram__bytes_write.sum"),
+                 "dram_bytes_per_launch": e.get("dram__bytes_read.sum", 0.0) + e.get("dram__bytes_write.sum", 0.0),
+                 "algorithmic_bytes_per_pass": 248 * 10000 * 5040, "ncu_ms": e.get("gpu__time_duration.sum"), "captured_at_commit": commit})
+# config 3: one pass = seed + local + carry + final; per-launch means of the four kernels, summed
+lr = {k: a for k, a in agg.items() if "lr_" in k}
+if lr:
+    recs.append({"workload": "c3", "symbols_": 500, "bars_": 1000000, "kernel": " + ".join(sorted(lr)),
+                 "dram_bytes_read": sum(a["rd"] / a["n"] for a in lr.values()), "dram_bytes_write": sum(a["wr"] / a["n"] for a in lr.values()),
+                 "dram_bytes_per_launch": sum((a["rd"] + a["wr"]) / a["n"] for a in lr.values()),
+                 "algorithmic_bytes_per_pass": 64 * 500 * 1000000, "ncu_ms": sum(a["ms"] / a["n"] for a in lr.values()),
+                 "captured_at_commit": commit})
 if recs and recs[0].get("symbols") == 50000:
     (ROOT / "gpurun_out" / "traffic.json").write_text(json.dumps(recs, indent=1) + "\n")
     print("wrote gpurun_out/traffic.json (copy to profiles/traffic.json)")
