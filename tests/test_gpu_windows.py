@@ -48,7 +48,7 @@ def test_window_suite_small_panels_and_listing_dates():
             assert nbad == 0, f"symbol {s}: {msg}"
     wp.close()
     # other shapes of the unit dealing: one window, no ATR, windows on both sides of the shared / global limit
-    for kdj, ext, atr in (((9,), (), 0), ((), (64, 65), 7), ((3, 100), (2,), 0)):
+    for kdj, ext, atr in (((9,), (), 0), ((), (64, 65), 7), ((3, 100), (2,), 0), ((33, 129), (40, 128, 499), 3), ((600,), (32, 33, 501), 0)):
         wp = WindowPanel(40, 500, kdj=kdj, ext=ext, atr=atr)
         wp.panel.set_fields(close=d["close"][:40, :500], high=d["high"][:40, :500], low=d["low"][:40, :500])
         res = wp.compute()
@@ -84,4 +84,29 @@ def test_config5_full_shape_against_the_oracle():
             for k, name in names.items():
                 nbad, msg = T.compare(name, outs[k][s], oks[k][s], refs[name][0], refs[name][1])
                 assert nbad == 0, f"block {b} symbol {s}: {msg}"
+    wp.close()
+
+
+def test_long_windows_ignore_nan_highs_and_lows_like_the_reference():
+    """The two-level window extremes (windows > 32) fold with the reference's f64::max / f64::min semantics (momentum.rs:644-650:
+    a NaN value is ignored), exactly like the one-level ones: willr / Donchian / midprice with NaN highs and lows."""
+    from polars_quant_b200.windows import WindowPanel
+    S, N = 33, 700
+    d = synth.ohlcv(S, N, seed=77)
+    h, l, c = d["high"].copy(), d["low"].copy(), d["close"].copy()
+    rng = np.random.default_rng(5)
+    for s in range(S):
+        idx = rng.choice(N, size=25, replace=False)
+        h[s, idx[:12]] = np.nan
+        l[s, idx[12:]] = np.nan
+    h[7, 100:420] = np.nan                      # longer than every window but one: whole windows without a comparable value
+    kdj, ext, atr = (), (20, 60, 250), 0
+    wp = WindowPanel(S, N, kdj=kdj, ext=ext, atr=atr)
+    wp.panel.set_fields(close=c, high=h, low=l)
+    res = wp.compute()
+    for s in (0, 7, 32):
+        for p in ext:
+            rv, rk = pqo.willr(h[s], l[s], c[s], p)
+            nbad, msg = T.compare("willr_%d" % p, res["willr_%d" % p][0][s], res["willr_%d" % p][1][s], rv, rk)
+            assert nbad == 0, f"symbol {s}: {msg}"
     wp.close()
