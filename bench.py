@@ -391,6 +391,24 @@ def main():
                "note": "caller-owned pageable column buffers -> thread-pool intake into pinned staging || chunked H2D || "
                        "pack + fused suite + unpack || D2H -> one Arrow struct array over the pinned result planes; PCIe-bound"}
         e2e_launches = hp.last_launches() * args.e2e_steps
+        # what the host <-> device link delivers on this box (all ranks at once, like the e2e step): the ceiling of the
+        # e2e device -> host leg, 21 result planes out while 4 input planes come in
+        gbs, perr = (C.c_double * 4)(), None
+        barrier()
+        try:
+            NV.check(NV.lib().pqb_probe_pcie(engine._h, 2 << 30, 3, gbs))
+        except Exception as ex:                             # (every rank still takes part in the collectives below)
+            perr = repr(ex)
+        barrier()
+        lo = [-x for x in max_over_ranks(*[-g for g in gbs])]                  # the slowest rank's rates
+        e2e["d2h_gbs_achieved"] = e2e["d2h_bytes_per_step"] / (e2e["ms_per_step"] * 1e-3) / 1e9
+        if perr or lo[2] <= 0:
+            e2e["pcie_probe"] = {"error": perr}
+        else:
+            e2e["pcie_probe"] = {"d2h_alone_gbs": lo[0], "h2d_alone_gbs": lo[1], "d2h_with_h2d_gbs": lo[2], "h2d_with_d2h_gbs": lo[3],
+                                 "how": "pqb_probe_pcie: 2 GiB pinned <-> device copies on the engine's own streams, every rank at the "
+                                        "same time, the slowest rank's rates; d2h_with_h2d_gbs bounds the e2e step's device -> host leg"}
+            e2e["d2h_frac_of_link"] = e2e["d2h_gbs_achieved"] / lo[2]
 
         # ---- CPU baseline on rank 0: the oracle port over a bounded sample of the same panel ----
         if rank == 0 and not args.no_cpu:

@@ -109,6 +109,10 @@ struct pqb_engine {
     std::mutex pool_mu;                  // guards live_panels / destroy_requested / the pool
     std::multimap<size_t, void *> host_pool;
     size_t host_pool_bytes = 0, host_pool_cap = 4ull << 30;
+    // ... and their device planes: cudaMalloc / cudaFree of ~60 buffers were 40 ms of a 130 ms WidePanel.suite() call on
+    // 2,000 x 2,520 (cudaFree synchronises the device); PQB_DEV_POOL_MB, default 4096
+    std::multimap<size_t, void *> dev_pool;
+    size_t dev_pool_bytes = 0, dev_pool_cap = 4ull << 30;
 };
 
 // page-locked host memory placed next to the engine's GPU (columns_host.inc: the calling thread runs on the GPU-local
@@ -148,6 +152,43 @@ static void host_give(pqb_engine *e, void *ptr, size_t bytes) {
         }
     }
     cudaFreeHost(ptr);
+}
+
+static cudaError_t dev_take(pqb_engine *e, void **out, size_t bytes) {
+    {
+        std::lock_guard<std::mutex> lk(e->pool_mu);
+        auto it = e->dev_pool.find(bytes);
+        if (it != e->dev_pool.end()) {
+            *out = it->second;
+            e->dev_pool.erase(it);
+            e->dev_pool_bytes -= bytes;
+            return cudaSuccess;
+        }
+    }
+    cudaError_t ce = cudaMalloc(out, bytes);
+    if (ce == cudaSuccess) return ce;
+    cudaGetLastError();
+    {                                                   // out of device memory: give the pool back and try once more
+        std::lock_guard<std::mutex> lk(e->pool_mu);
+        for (auto &kv : e->dev_pool) cudaFree(kv.second);
+        e->dev_pool.clear();
+        e->dev_pool_bytes = 0;
+    }
+    return cudaMalloc(out, bytes);
+}
+
+// (the caller has synchronised the streams that used the buffer: a pooled buffer is handed out again without a device sync)
+static void dev_give(pqb_engine *e, void *ptr, size_t bytes) {
+    if (!ptr) return;
+    if (e) {
+        std::lock_guard<std::mutex> lk(e->pool_mu);
+        if (e->dev_pool_bytes + bytes <= e->dev_pool_cap) {
+            e->dev_pool.emplace(bytes, ptr);
+            e->dev_pool_bytes += bytes;
+            return;
+        }
+    }
+    cudaFree(ptr);
 }
 
 struct pqb_panel {
@@ -226,6 +267,7 @@ extern "C" int pqb_engine_create(int device, pqb_engine **out) {
     e->device = device;
     e->sm_count = pr.multiProcessorCount;
     if (const char *hp = getenv("PQB_HOST_POOL_MB")) e->host_pool_cap = (size_t)std::max(0, atoi(hp)) << 20;   // 0: no pooling
+    if (const char *dp = getenv("PQB_DEV_POOL_MB")) e->dev_pool_cap = (size_t)std::max(0, atoi(dp)) << 20;
     CU(cudaSetDevice(device));
     CU(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&e->h2d, cudaStreamNonBlocking));
@@ -249,6 +291,7 @@ extern "C" int pqb_engine_create(int device, pqb_engine **out) {
 static void engine_free(pqb_engine *e) {
     cudaSetDevice(e->device);
     for (auto &kv : e->host_pool) cudaFreeHost(kv.second);
+    for (auto &kv : e->dev_pool) cudaFree(kv.second);
     if (e->flush_buf) cudaFree(e->flush_buf);
     if (e->stream) cudaStreamDestroy(e->stream);
     if (e->h2d) cudaStreamDestroy(e->h2d);
@@ -319,18 +362,18 @@ extern "C" int pqb_panel_create(pqb_engine *e, int64_t n_symbols, int64_t n_bars
     cudaError_t ce;
     for (int f = 0; f < PQB_N_FIELDS; ++f) {
         if (!(fields_mask >> f & 1)) continue;
-        if ((ce = cudaMalloc(&p->d_in[f], dplane)) != cudaSuccess) return bail(ce, "cudaMalloc(field)");
+        if ((ce = dev_take(e, (void **)&p->d_in[f], dplane)) != cudaSuccess) return bail(ce, "cudaMalloc(field)");
         if ((ce = cudaMemsetAsync(p->d_in[f], 0, dplane, e->stream)) != cudaSuccess) return bail(ce, "memset");
         p->in_slot[f] = p->n_in_alloc++;
         if (p->staging) {
             if ((ce = host_take(e, (void **)&p->h_in[f], hplane)) != cudaSuccess) return bail(ce, "cudaMallocHost(field)");
-            memset(p->h_in[f], 0, hplane);
+            if (host_staging != 2) memset(p->h_in[f], 0, hplane);
         }
     }
     for (int k = 0; k < PQB_N_OUTPUTS; ++k) {
         if (!(outputs_mask >> k & 1)) continue;
-        if ((ce = cudaMalloc(&p->d_out[k], dplane)) != cudaSuccess) return bail(ce, "cudaMalloc(output)");
-        if ((ce = cudaMalloc(&p->d_bits[k], bplane)) != cudaSuccess) return bail(ce, "cudaMalloc(validity)");
+        if ((ce = dev_take(e, (void **)&p->d_out[k], dplane)) != cudaSuccess) return bail(ce, "cudaMalloc(output)");
+        if ((ce = dev_take(e, (void **)&p->d_bits[k], bplane)) != cudaSuccess) return bail(ce, "cudaMalloc(validity)");
         p->out_slot[k] = p->n_out_alloc++;
         if (p->staging) {
             if ((ce = host_take(e, (void **)&p->h_out[k], hplane)) != cudaSuccess) return bail(ce, "cudaMallocHost(output)");
@@ -345,9 +388,9 @@ extern "C" int pqb_panel_create(pqb_engine *e, int64_t n_symbols, int64_t n_bars
         p->chunk_symbols = cs;
         const size_t cplane = (size_t)cs * p->pitch * sizeof(double);
         for (int b = 0; b < 2; ++b) {
-            if ((ce = cudaMalloc(&p->d_xin[b], cplane * p->n_in_alloc)) != cudaSuccess) return bail(ce, "cudaMalloc(xfer in)");
+            if ((ce = dev_take(e, (void **)&p->d_xin[b], cplane * p->n_in_alloc)) != cudaSuccess) return bail(ce, "cudaMalloc(xfer in)");
             if (p->n_out_alloc &&
-                (ce = cudaMalloc(&p->d_xout[b], cplane * p->n_out_alloc)) != cudaSuccess) return bail(ce, "cudaMalloc(xfer out)");
+                (ce = dev_take(e, (void **)&p->d_xout[b], cplane * p->n_out_alloc)) != cudaSuccess) return bail(ce, "cudaMalloc(xfer out)");
             if ((ce = cudaEventCreateWithFlags(&p->ev_packed[b], cudaEventDisableTiming)) != cudaSuccess) return bail(ce, "event");
             if ((ce = cudaEventCreateWithFlags(&p->ev_d2h[b], cudaEventDisableTiming)) != cudaSuccess) return bail(ce, "event");
         }
@@ -368,11 +411,22 @@ extern "C" void pqb_panel_destroy(pqb_panel *p) {
     if (!p) return;
     if (p->refs.fetch_sub(1) > 1) return;            // exports still alias the result planes: the last release frees
     if (p->e) cudaSetDevice(p->e->device);
-    for (auto &q : p->d_in) if (q) cudaFree(q);
-    for (auto &q : p->d_out) if (q) cudaFree(q);
-    for (auto &q : p->d_bits) if (q) cudaFree(q);
-    for (auto &q : p->d_xin) if (q) cudaFree(q);
-    for (auto &q : p->d_xout) if (q) cudaFree(q);
+    // the big planes go back to the engine's device pool (dev_give): nothing may still be running on them
+    if (p->e) {
+        cudaStreamSynchronize(p->e->stream);
+        cudaStreamSynchronize(p->e->h2d);
+        cudaStreamSynchronize(p->e->d2h);
+    }
+    {
+        const size_t dplane_ = p->plane_doubles * sizeof(double);
+        const size_t bplane_ = (size_t)p->n_symbols * p->words_per_row * sizeof(uint32_t);
+        const size_t cplane_ = (size_t)p->chunk_symbols * p->pitch * sizeof(double);
+        for (auto &q : p->d_in) dev_give(p->e, q, dplane_);
+        for (auto &q : p->d_out) dev_give(p->e, q, dplane_);
+        for (auto &q : p->d_bits) dev_give(p->e, q, bplane_);
+        for (auto &q : p->d_xin) dev_give(p->e, q, cplane_ * p->n_in_alloc);
+        for (auto &q : p->d_xout) dev_give(p->e, q, cplane_ * p->n_out_alloc);
+    }
     if (p->d_start) cudaFree(p->d_start);
     for (auto &q : p->d_vin) if (q) cudaFree(q);
     for (auto &q : p->d_ovm) if (q) cudaFree(q);
@@ -634,6 +688,14 @@ static bool split_launch_enabled() {
     return !s || atoi(s) != 0;
 }
 
+// panels of up to this many symbol blocks run the small-panel variant of the full suite (nine pipelined role warps, two
+// CTAs per SM); PQB_SMALL_BLOCKS overrides (tuning)
+static int64_t small_max_blocks(const pqb_engine *e) {
+    static const char *ev = getenv("PQB_SMALL_BLOCKS");
+    if (ev) return atoll(ev);
+    return e->sm_count + e->sm_count / N_ROLES_X;
+}
+
 // shared-memory ring layout of one launch: offsets of every enabled group's rings / van Herk arrays and the dynamic
 // shared-memory size (depends on A.gmask and the periods only, so a launch of a subset of the groups gets its own)
 static int layout_rings(SuiteArgs &A, const pqb_panel *p) {
@@ -648,7 +710,7 @@ static int layout_rings(SuiteArgs &A, const pqb_panel *p) {
     const bool partial_spare = !(A.gmask & ~(unsigned)G_ALL) && A.gmask != (unsigned)G_ALL && active_roles < N_ROLES &&
                                p->n_blocks <= 3ll * p->e->sm_count;
     A.mid_own = (A.gmask & G_MIDPRICE) &&
-                (!mid_shares || partial_spare || (A.gmask == G_ALL && p->n_blocks <= p->e->sm_count + p->e->sm_count / N_ROLES_X));
+                (!mid_shares || partial_spare || (A.gmask == G_ALL && p->n_blocks <= small_max_blocks(p->e)));
 retry_layout:
     long long off = 0;
     auto take = [&](int slots) { const long long o = off; off += (long long)std::max(slots, 1) * SYM; return (int)std::min<long long>(o, 1ll << 30); };
@@ -1024,6 +1086,12 @@ static SuiteArgs null_variant(const pqb_panel *p, SuiteArgs a) {
     return a;
 }
 
+// tuning: PQB_FULLS_SMEM = dynamic shared memory requested for the full-suite kernel (more than it needs = fewer CTAs per SM)
+static int fulls_smem(int need) {
+    static const char *ev = getenv("PQB_FULLS_SMEM");
+    return ev ? std::max(need, atoi(ev)) : need;
+}
+
 // Launches the suite over symbol blocks [b0, b0+nb) (+ NaN fills + validity bitmaps of those symbols).
 static int launch_suite(pqb_panel *p, const Built &full, int64_t b0, int64_t nb, cudaEvent_t ev_after_fused,
                         int *launches) {
@@ -1067,7 +1135,7 @@ static int launch_suite(pqb_panel *p, const Built &full, int64_t b0, int64_t nb,
         const char *ps = getenv("PQB_PIPELINE");
         const bool pipe_ok = !ps || atoi(ps) != 0;
         // the small-panel variant: nine role warps (two CTAs of 320 threads fit an SM)
-        const bool small = fulls && pipe_ok && !a.vmask && a.mid_own && nb <= e->sm_count + e->sm_count / N_ROLES_X;
+        const bool small = fulls && pipe_ok && !a.vmask && a.mid_own && nb <= small_max_blocks(e);
         // a launch of optional groups only: the general kernel with its seven warps dealt as slots (suite_kernel.cuh)
         const char *ws = getenv("PQB_WIDE");
         const bool wide = !a.vmask && a.gmask && !(a.gmask & (unsigned)G_ALL) && (!ws || atoi(ws) != 0);
@@ -1086,7 +1154,7 @@ static int launch_suite(pqb_panel *p, const Built &full, int64_t b0, int64_t nb,
         // plain one (the pipelined loops execute more instructions)
         else if (small)
             suite_fused_kernel<true, false, false, true><<<grid, CTA_THREADS_X, a.smem_bytes, e->stream>>>(a);
-        else if (fulls) suite_fused_kernel<true, false><<<grid, CTA_THREADS, a.smem_bytes, e->stream>>>(a);
+        else if (fulls) suite_fused_kernel<true, false><<<grid, CTA_THREADS, fulls_smem(a.smem_bytes), e->stream>>>(a);
         else if (!(a.gmask & ~(unsigned)G_ALL) && !fastk) {
             deal_base_slots(a);
             suite_fused_kernel<false, false, true><<<grid, CTA_THREADS, a.smem_bytes, e->stream>>>(a);
@@ -1477,6 +1545,62 @@ __global__ void __launch_bounds__(256) stream_mix_kernel(const __grid_constant__
         for (int f = 0; f < P.n_in; ++f) s += __ldcs(P.in[f] + i);
         for (int k = 0; k < P.n_out; ++k) __stcs(P.out[k] + i, s + (double)k);
     }
+}
+
+extern "C" int pqb_probe_pcie(pqb_engine *e, int64_t bytes, int iters, double gbs[4]) {
+    if (!e || !gbs || bytes < (1 << 20) || iters < 1) return fail(PQB_ERR_INVALID, "pqb_probe_pcie: bad argument");
+    int rc = set_dev(e);
+    if (rc) return rc;
+    const size_t out_b = (size_t)bytes, in_b = (size_t)bytes * 4 / 21 / 256 * 256;
+    void *h_out = nullptr, *h_in = nullptr, *d_out = nullptr, *d_in = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    auto release = [&]() {
+        if (h_out) host_give(e, h_out, out_b);
+        if (h_in) host_give(e, h_in, in_b);
+        if (d_out) cudaFree(d_out);
+        if (d_in) cudaFree(d_in);
+        for (auto &x : ev) if (x) cudaEventDestroy(x);
+    };
+    cudaError_t ce = host_take(e, &h_out, out_b);
+    if (ce == cudaSuccess) ce = host_take(e, &h_in, in_b);
+    if (ce == cudaSuccess) ce = cudaMalloc(&d_out, out_b);
+    if (ce == cudaSuccess) ce = cudaMalloc(&d_in, in_b);
+    for (auto &x : ev) if (ce == cudaSuccess) ce = cudaEventCreate(&x);
+    if (ce != cudaSuccess) { release(); cudaGetLastError(); return fail(PQB_ERR_ALLOC, "pqb_probe_pcie: %s", cudaGetErrorString(ce)); }
+    memset(h_in, 0, in_b);
+    cudaMemsetAsync(d_out, 0, out_b, e->d2h);
+    auto down = [&]() { return cudaMemcpyAsync(h_out, d_out, out_b, cudaMemcpyDeviceToHost, e->d2h); };
+    auto up = [&]() { return cudaMemcpyAsync(d_in, h_in, in_b, cudaMemcpyHostToDevice, e->h2d); };
+    down(); up();                                          // touch everything once
+    cudaStreamSynchronize(e->d2h); cudaStreamSynchronize(e->h2d);
+    float ms = 0.f;
+    cudaEventRecord(ev[0], e->d2h);
+    for (int i = 0; i < iters; ++i) down();
+    cudaEventRecord(ev[1], e->d2h);
+    cudaEventSynchronize(ev[1]);
+    cudaEventElapsedTime(&ms, ev[0], ev[1]);
+    gbs[0] = (double)out_b * iters / (ms * 1e-3) / 1e9;
+    cudaEventRecord(ev[2], e->h2d);
+    for (int i = 0; i < iters; ++i) up();
+    cudaEventRecord(ev[3], e->h2d);
+    cudaEventSynchronize(ev[3]);
+    cudaEventElapsedTime(&ms, ev[2], ev[3]);
+    gbs[1] = (double)in_b * iters / (ms * 1e-3) / 1e9;
+    cudaEventRecord(ev[0], e->d2h);
+    cudaEventRecord(ev[2], e->h2d);
+    for (int i = 0; i < iters; ++i) { down(); up(); }
+    cudaEventRecord(ev[1], e->d2h);
+    cudaEventRecord(ev[3], e->h2d);
+    cudaEventSynchronize(ev[1]);
+    cudaEventSynchronize(ev[3]);
+    cudaEventElapsedTime(&ms, ev[0], ev[1]);
+    gbs[2] = (double)out_b * iters / (ms * 1e-3) / 1e9;
+    cudaEventElapsedTime(&ms, ev[2], ev[3]);
+    gbs[3] = (double)in_b * iters / (ms * 1e-3) / 1e9;
+    ce = cudaGetLastError();
+    release();
+    if (ce != cudaSuccess) return fail(PQB_ERR_CUDA, "pqb_probe_pcie: %s", cudaGetErrorString(ce));
+    return PQB_OK;
 }
 
 extern "C" int pqb_stream_mix(pqb_engine *e, int n_reads, int n_writes, int64_t doubles_per_plane, int warmup, int iters,

@@ -60,7 +60,7 @@ class Panel:
         self.host_staging = host_staging
         self._h = C.c_void_p()
         N.check(N.lib().pqb_panel_create(self.engine._h, n_symbols, n_bars, fields_mask, outputs_mask,
-                                         1 if host_staging else 0, C.byref(self._h)))
+                                         int(host_staging) if host_staging else 0, C.byref(self._h)))
         self.pitch = N.lib().pqb_panel_pitch(self._h)
         self.validity_pitch = N.lib().pqb_panel_validity_pitch(self._h)
 

@@ -208,6 +208,81 @@ class _Keep:
         self.owner = owner
 
 
+class WideResult:
+    """The result of `WidePanel.suite(lazy=True)`: the `{symbol}_{output}` columns of a run, made on demand as Arrow arrays
+    that alias the pinned result planes (no copy; an array keeps its panel alive).  A 2,000-symbol suite has 42,000 result
+    columns: wrapping every one of them in Arrow objects costs more host time than the GPU pass (pyarrow needs ~1 us per
+    column and per operation), so the wide table is only built when `table()` is called.
+
+        res = wp.suite(lazy=True)
+        res["AAPL_rsi"]            # pyarrow Float64 array (values + validity straight from the pinned planes)
+        res.symbol("AAPL")         # {"sma": array, "ema": array, ...}
+        res.matrix("rsi")          # (values [n_symbols, n_bars] numpy view, validity bool [n_symbols, n_bars])
+        res.table()                # the full `date` + `{symbol}_{output}` pyarrow table"""
+
+    def __init__(self, shards, symbols, names, omask, n_bars, dates):
+        self._shards = shards                  # [(Panel, lo, hi)]
+        # (columns in the order of the table: by symbol, then by output id)
+        self.symbols, self.outputs = list(symbols), sorted(names, key=N.OUTPUT_NAMES.index)
+        self._omask, self.n_bars, self.dates = omask, n_bars, dates
+        self._row = {s: i for i, s in enumerate(self.symbols)}
+        self._by_len = sorted(self.outputs, key=len, reverse=True)
+
+    def __len__(self):
+        return len(self.symbols) * len(self.outputs)
+
+    @property
+    def column_names(self):
+        return ["%s_%s" % (s, o) for s in self.symbols for o in self.outputs]
+
+    def _locate(self, row):
+        for p, lo, hi in self._shards:
+            if lo <= row < hi:
+                return p, row - lo
+        raise KeyError(row)
+
+    def array(self, symbol: str, output: str) -> pa.Array:
+        p, r = self._locate(self._row[symbol])
+        k = N.OUTPUT_NAMES.index(output)
+        if output not in self.outputs:
+            raise KeyError(output)
+        base = _Keep(p)
+        vals = N.lib().pqb_panel_host_output(p._h, k) + r * p.pitch * 8
+        bits = N.lib().pqb_panel_host_validity(p._h, k) + r * p.validity_pitch
+        return pa.Array.from_buffers(pa.float64(), self.n_bars, [pa.foreign_buffer(bits, (self.n_bars + 7) // 8, base),
+                                                                 pa.foreign_buffer(vals, self.n_bars * 8, base)])
+
+    def __getitem__(self, name: str) -> pa.Array:
+        for o in self._by_len:                 # `{symbol}_{output}`: symbols may contain underscores themselves
+            if name.endswith("_" + o) and name[:-len(o) - 1] in self._row:
+                return self.array(name[:-len(o) - 1], o)
+        raise KeyError(name)
+
+    def symbol(self, symbol: str) -> dict:
+        return {o: self.array(symbol, o) for o in self.outputs}
+
+    def matrix(self, output: str):
+        """(values, validity) of one output for every symbol, rows in `symbols` order (numpy; one shard: views)."""
+        k = N.OUTPUT_NAMES.index(output)
+        vs = [p.host_output(k) for p, _, _ in self._shards]
+        oks = [p.host_validity(k) for p, _, _ in self._shards]
+        return (vs[0], oks[0]) if len(vs) == 1 else (np.concatenate(vs), np.concatenate(oks))
+
+    def table(self) -> pa.Table:
+        batches = [p.export_arrow(self._omask, self.symbols[lo:hi]) for p, lo, hi in self._shards]
+        if len(batches) == 1:
+            out = pa.Table.from_batches(batches)
+        else:
+            cols, names = [], []
+            for rb in batches:
+                cols.extend(rb.columns)
+                names.extend(rb.schema.names)
+            out = pa.table(cols, names=names)
+        if self.dates is not None:
+            out = out.add_column(0, "date", self.dates)
+        return out
+
+
 class WidePanel:
     """A wide `date` + `{symbol}_{column}` table on one B200."""
 
@@ -220,6 +295,7 @@ class WidePanel:
         self._suite = None
         self._candles = None
         self._batch = None
+        self._exported = None
         self.last_timings = {}
 
     def _col(self, name):
@@ -247,19 +323,35 @@ class WidePanel:
         self._batch._export_to_c(C.addressof(arr), C.addressof(sch))
         return arr, sch
 
+    def _record_batch_cached(self):
+        """One export for the life of this WidePanel (the table is immutable): exporting 10,001 columns through the C Data
+        Interface costs ~5 ms per call.  The engine only borrows the batch (it never calls release)."""
+        if self._exported is None:
+            self._exported = self._record_batch()
+        return self._exported
+
+    def __del__(self):
+        try:
+            if self._exported is not None:
+                self._release(*self._exported)
+                self._exported = None
+        except Exception:
+            pass
+
     @staticmethod
     def _release(arr, sch):
         for x, proto in ((arr, C.CFUNCTYPE(None, C.POINTER(N.ArrowArray))), (sch, C.CFUNCTYPE(None, C.POINTER(N.ArrowSchema)))):
             if x.release:
                 proto(x.release)(C.pointer(x))
 
-    def suite(self, params: N.SuiteParams | None = None, outputs=None, threads: int = 0, devices=None) -> pa.Table:
+    def suite(self, params: N.SuiteParams | None = None, outputs=None, threads: int = 0, devices=None, lazy: bool = False):
         """Runs the fused suite over every symbol that has close / high / low / volume columns; returns `date` +
         `{symbol}_{output}` for the requested output names (default: the 21 suite outputs).  The table crosses the C ABI
         as ONE Arrow record batch (pqb_suite_run_record_batch: intake pipelined with the GPU pipeline) and the results
         come back as ONE record batch aliasing the pinned result planes (pqb_panel_export_arrow) -- no per-column work in
         Python.  `devices`: GPU ordinals to shard the symbols over (contiguous ranges, one host thread per GPU, no
-        collective -- SURVEY.md 8e); default: this panel's engine only."""
+        collective -- SURVEY.md 8e); default: this panel's engine only.  `lazy=True` returns a `WideResult` (columns wrapped
+        on demand) instead of the full table."""
         import time
         tm = self.last_timings = {}
         t_ = time.perf_counter()
@@ -295,21 +387,18 @@ class WidePanel:
             eng, lo, hi = shards[i]
             try:
                 t0 = time.perf_counter()
-                p = Panel(hi - lo, self.n_bars, engine=eng, outputs_mask=omask)
+                p = Panel(hi - lo, self.n_bars, engine=eng, outputs_mask=omask, host_staging=2)     # (every row is staged below)
                 tm["panel_create_ms"] = tm.get("panel_create_ms", 0.0) + (time.perf_counter() - t0) * 1e3
                 mine = (fld >= 0) & (sym >= lo) & (sym < hi)
                 s_i = np.ascontiguousarray(np.where(mine, sym - lo, 0), dtype=np.int64)
                 f_i = np.ascontiguousarray(np.where(mine, fld, -1), dtype=np.int32)
                 t0 = time.perf_counter()
-                arr, sch = self._record_batch()
+                arr, sch = self._record_batch_cached()
                 t1 = time.perf_counter()
-                try:
-                    N.check(N.lib().pqb_suite_run_record_batch(p._h, C.byref(params), C.byref(arr), C.byref(sch), s_i.ctypes.data,
-                                                               f_i.ctypes.data, threads))
-                finally:
-                    self._release(arr, sch)
+                N.check(N.lib().pqb_suite_run_record_batch(p._h, C.byref(params), C.byref(arr), C.byref(sch), s_i.ctypes.data,
+                                                           f_i.ctypes.data, threads))
                 t2 = time.perf_counter()
-                batches[i] = (p, p.export_arrow(omask, symbols[lo:hi]))
+                batches[i] = (p, None if lazy else p.export_arrow(omask, symbols[lo:hi]))
                 t3 = time.perf_counter()
                 for k, v in (("export_input_batch_ms", t1 - t0), ("run_record_batch_ms", t2 - t1), ("export_results_ms", t3 - t2)):
                     tm[k] = tm.get(k, 0.0) + v * 1e3
@@ -329,6 +418,10 @@ class WidePanel:
             raise errors[0]
         t_ = time.perf_counter()
         self._suite = [p for p, _ in batches]
+        if lazy:
+            res = WideResult([(b[0], sh[1], sh[2]) for b, sh in zip(batches, shards)], symbols, names, omask, self.n_bars, self.dates)
+            lap("assemble_table_ms")
+            return res
         if len(batches) == 1:
             out = pa.Table.from_batches([batches[0][1]])
         else:

@@ -54,6 +54,31 @@ def test_wide_suite_matches_the_oracle_per_symbol(tmp_path):
     assert out["AAA_sma"].null_count >= 29 and np.isfinite(out["AAA_sma"][100].as_py())
 
 
+def test_lazy_result_columns_are_the_table_columns(tmp_path):
+    """`suite(lazy=True)`: columns wrapped on demand over the pinned planes are the columns of the full table, bit for bit and
+    null for null; repeated calls reuse pooled planes (a result must keep ITS panel's memory, not the next call's)."""
+    for k, days in enumerate((range(0, 300), range(40, 300), [d for d in range(0, 300) if d != 150])):
+        pq.write_table(_symbol_table(10 + k, list(days)), tmp_path / ("S_%d.parquet" % k))          # (symbols with an underscore)
+    t = wide.load(tmp_path)
+    wp = wide.WidePanel(t)
+    names = ["sma", "bb_upper", "macd_signal", "kdj_j", "obv"]
+    full = wp.suite(outputs=names)
+    lazy = wp.suite(outputs=names, lazy=True)
+    again = wp.suite(outputs=names, lazy=True)           # a third panel while the first two results are alive
+    assert lazy.symbols == ["S_0", "S_1", "S_2"] and sorted(lazy.outputs) == sorted(names) and len(lazy) == 15
+    assert lazy.column_names == full.column_names[1:]
+    for res in (lazy, again):
+        for name in res.column_names:
+            a, b = res[name], full[name].combine_chunks()
+            assert a.null_count == b.null_count and a.equals(b), name
+    v, ok = lazy.matrix("sma")
+    assert v.shape == (3, 300) and np.array_equal(ok[0], ~np.asarray(full["S_0_sma"].combine_chunks().is_null()))
+    assert set(lazy.symbol("S_1")) == set(names)
+    assert lazy.table().equals(full)
+    with pytest.raises(KeyError):
+        lazy["S_0_rsi"]
+
+
 def test_wide_candles_and_null_refusal(tmp_path):
     pq.write_table(_symbol_table(5, list(range(0, 300))), tmp_path / "AAA.parquet")
     pq.write_table(_symbol_table(6, list(range(50, 300))), tmp_path / "BBB.parquet")
