@@ -249,7 +249,7 @@ def main():
     ap.add_argument("--no-extra", action="store_true", help="skip the kernel-only lines of the other shapes (configs 2, 3, 5, candles)")
     ap.add_argument("--e2e-symbols", type=int, default=0, help="symbols per GPU pushed through the column API (0: the GPU's whole share)")
     ap.add_argument("--e2e-steps", type=int, default=3)
-    ap.add_argument("--threads", type=int, default=0, help="host threads of the column intake per GPU (0: cores / GPUs, at most 16)")
+    ap.add_argument("--threads", type=int, default=0, help="host threads of the column intake per GPU (0: cores / GPUs, at most 6)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
@@ -345,7 +345,7 @@ def main():
     if not args.no_e2e:
         import ctypes as C
         Se = min(S, args.e2e_symbols) if args.e2e_symbols else S
-        threads = args.threads or max(1, min(16, (os.cpu_count() or 1) // max(world, 1)))
+        threads = args.threads or max(2, min(6, (os.cpu_count() or 1) // max(world, 1)))   # (more only fights the DMA for the memory bus)
         hp = None
         while hp is None:
             try:

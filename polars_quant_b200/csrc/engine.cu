@@ -191,10 +191,15 @@ static void dev_give(pqb_engine *e, void *ptr, size_t bytes) {
     cudaFree(ptr);
 }
 
+struct pqb_panel;
+static void export_cache_drop(pqb_panel *p);
+
 struct pqb_panel {
     // the panel itself holds one reference, every outstanding Arrow export (pqb_panel_export_arrow) another: the
     // pinned result planes an export aliases live until the last of them is released
     std::atomic<int> refs{1};
+    std::mutex export_mu;                // the vectors of a released Arrow export, kept for the next one (columns_host.inc)
+    void *export_cache_a = nullptr, *export_cache_s = nullptr;
     pqb_engine *e = nullptr;
     int64_t n_symbols = 0, n_bars = 0, pitch = 0, words_per_row = 0;
     int64_t n_blocks = 0, bars_padded = 0;   // tiled geometry
@@ -410,6 +415,7 @@ extern "C" int pqb_panel_create(pqb_engine *e, int64_t n_symbols, int64_t n_bars
 extern "C" void pqb_panel_destroy(pqb_panel *p) {
     if (!p) return;
     if (p->refs.fetch_sub(1) > 1) return;            // exports still alias the result planes: the last release frees
+    export_cache_drop(p);
     if (p->e) cudaSetDevice(p->e->device);
     // the big planes go back to the engine's device pool (dev_give): nothing may still be running on them
     if (p->e) {
