@@ -1153,6 +1153,13 @@ static int launch_suite(pqb_panel *p, const Built &full, int64_t b0, int64_t nb,
             a.split_from = e->sm_count;
             grid = (unsigned)(e->sm_count + (nb - e->sm_count) * parts);
         }
+        // tuning: PQB_SPLIT_ALL=<parts> splits EVERY block of a launch between one and two CTAs per SM into that many CTAs
+        static const int split_all = getenv("PQB_SPLIT_ALL") ? atoi(getenv("PQB_SPLIT_ALL")) : 0;
+        if (split_all > 1 && fulls && !small && nb > e->sm_count + e->sm_count / nr && nb < 2ll * e->sm_count) {
+            a.split_from = 0;
+            a.split_parts = std::min(nr, split_all);
+            grid = (unsigned)(nb * a.split_parts);
+        }
         if (a.vmask) suite_fused_kernel<false, true><<<grid, CTA_THREADS, a.smem_bytes, e->stream>>>(a);
         // small panels (about one CTA per SM) are bound by the length of each role's dependent FP64 chain per bar, not by
         // issue slots or HBM: they run the variant whose division-heavy roles (BBANDS, RSI, STOCH) are software-pipelined
