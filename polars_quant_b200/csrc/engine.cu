@@ -93,6 +93,8 @@ struct pqb_engine {
     int sm_count = 0;
     cudaStream_t stream = nullptr;       // compute
     cudaStream_t h2d = nullptr, d2h = nullptr;
+    cudaStream_t aux = nullptr;          // the compact tail launch of a small panel runs beside the main launch (launch_suite)
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     void *flush_buf = nullptr;
     size_t flush_bytes = 0;
     std::mutex mu;                       // guards the single-column scratch panel
@@ -276,6 +278,9 @@ extern "C" int pqb_engine_create(int device, pqb_engine **out) {
     CU(cudaSetDevice(device));
     CU(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&e->h2d, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&e->aux, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
     CU(cudaStreamCreateWithFlags(&e->d2h, cudaStreamNonBlocking));
     CU(cudaFuncSetAttribute(suite_fused_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
     CU(cudaFuncSetAttribute(suite_fused_kernel<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
@@ -300,6 +305,9 @@ static void engine_free(pqb_engine *e) {
     if (e->flush_buf) cudaFree(e->flush_buf);
     if (e->stream) cudaStreamDestroy(e->stream);
     if (e->h2d) cudaStreamDestroy(e->h2d);
+    if (e->aux) cudaStreamDestroy(e->aux);
+    if (e->ev_fork) cudaEventDestroy(e->ev_fork);
+    if (e->ev_join) cudaEventDestroy(e->ev_join);
     if (e->d2h) cudaStreamDestroy(e->d2h);
     delete e;
 }
@@ -696,9 +704,24 @@ static bool split_launch_enabled() {
 
 // panels of up to this many symbol blocks run the small-panel variant of the full suite (nine pipelined role warps, two
 // CTAs per SM); PQB_SMALL_BLOCKS overrides (tuning)
+// CTAs per tail block: as many as keeps the tail launch at about half a CTA per SM (measured, profiles/r03a_compact_tail.txt:
+// 9 tail blocks -> one role per CTA, 24 -> three roles per CTA; more tail CTAs than that cost more than they spread)
+static int tail_parts_compact(const pqb_engine *e, int64_t n_tail) {
+    static const int forced = getenv("PQB_TAIL_PARTS") ? std::max(1, std::min((int)N_ROLES_X, atoi(getenv("PQB_TAIL_PARTS")))) : 0;
+    if (forced) return forced;
+    const int64_t by_budget = (e->sm_count * 55ll / 100) / std::max<int64_t>(n_tail, 1);
+    return (int)std::max<int64_t>(2, std::min<int64_t>(N_ROLES_X, by_budget));
+}
+static bool tail_compact() {
+    static const bool v = !getenv("PQB_TAIL_COMPACT") || atoi(getenv("PQB_TAIL_COMPACT")) != 0;
+    return v;
+}
 static int64_t small_max_blocks(const pqb_engine *e) {
     static const char *ev = getenv("PQB_SMALL_BLOCKS");
     if (ev) return atoll(ev);
+    // one whole-block CTA per SM + up to sm_count / 5 blocks beyond as compact tail CTAs (beyond that the plain kernel with two
+    // CTAs on some SMs is as fast: 196 blocks 1.61 against 1.59 ms)
+    if (tail_compact()) return e->sm_count + e->sm_count / 5;
     return e->sm_count + e->sm_count / N_ROLES_X;
 }
 
@@ -1098,6 +1121,11 @@ static int fulls_smem(int need) {
     return ev ? std::max(need, atoi(ev)) : need;
 }
 
+static bool force_base() {
+    static const bool v = getenv("PQB_FORCE_BASE") && atoi(getenv("PQB_FORCE_BASE")) != 0;
+    return v;
+}
+
 // Launches the suite over symbol blocks [b0, b0+nb) (+ NaN fills + validity bitmaps of those symbols).
 static int launch_suite(pqb_panel *p, const Built &full, int64_t b0, int64_t nb, cudaEvent_t ev_after_fused,
                         int *launches) {
@@ -1146,10 +1174,11 @@ static int launch_suite(pqb_panel *p, const Built &full, int64_t b0, int64_t nb,
         const char *ws = getenv("PQB_WIDE");
         const bool wide = !a.vmask && a.gmask && !(a.gmask & (unsigned)G_ALL) && (!ws || atoi(ws) != 0);
         const int nr = small ? N_ROLES_X : wide ? N_SLOTS_W : N_ROLES;
-        int parts = nr;                                       // tail CTAs per split block (default: one role each)
-        if (const char *tp = getenv("PQB_TAIL_PARTS")) parts = std::max(1, std::min(nr, atoi(tp)));
+        int parts = nr;                                       // in-grid tail CTAs per split block (default: one role each)
+        if (const char *tp = getenv("PQB_TAIL_PARTS")) if (!tail_compact()) parts = std::max(1, std::min(nr, atoi(tp)));
         a.split_parts = parts;
-        if (tail_ok && nb > e->sm_count && nb <= e->sm_count + e->sm_count / nr) {
+        a.split_compact = 0;
+        if (tail_ok && nb > e->sm_count && nb <= e->sm_count + e->sm_count / nr && !(small && tail_compact())) {
             a.split_from = e->sm_count;
             grid = (unsigned)(e->sm_count + (nb - e->sm_count) * parts);
         }
@@ -1165,8 +1194,31 @@ static int launch_suite(pqb_panel *p, const Built &full, int64_t b0, int64_t nb,
         // issue slots or HBM: they run the variant whose division-heavy roles (BBANDS, RSI, STOCH) are software-pipelined
         // over bars (suite_kernel.cuh "software-pipelined steady bar"); large panels are throughput-bound and run the
         // plain one (the pipelined loops execute more instructions)
+        else if (small && tail_compact() && tail_ok && nb > e->sm_count) {
+            // one whole-block CTA per SM; the blocks beyond run beside them as COMPACT tail CTAs (a launch of its own on a
+            // second stream: `parts` CTAs per block, each 32 * (roles per CTA + 1) threads with its own producer and ring),
+            // so a tail CTA holds 4 warps of registers instead of 10 and the block scheduler can put two of them next to a
+            // whole-block CTA -- no SM walks two whole blocks
+            const int cp = tail_parts_compact(e, nb - e->sm_count);
+            SuiteArgs m = a, t = a;
+            m.split_from = -1;
+            t.split_from = 0; t.split_parts = cp; t.split_compact = 1;
+            if (t.blist) t.blist += e->sm_count; else t.block0 += e->sm_count;
+            const int roles_per_cta = (N_ROLES_X + cp - 1) / cp;
+            CU(cudaEventRecord(e->ev_fork, e->stream));
+            CU(cudaStreamWaitEvent(e->aux, e->ev_fork, 0));
+            suite_fused_kernel<true, false, false, true><<<(unsigned)e->sm_count, CTA_THREADS_X, m.smem_bytes, e->stream>>>(m);
+            suite_fused_kernel<true, false, false, true><<<(unsigned)((nb - e->sm_count) * cp), 32 * (roles_per_cta + 1), t.smem_bytes, e->aux>>>(t);
+            CU(cudaEventRecord(e->ev_join, e->aux));
+            CU(cudaStreamWaitEvent(e->stream, e->ev_join, 0));
+            ++n_launch;
+        }
         else if (small)
             suite_fused_kernel<true, false, false, true><<<grid, CTA_THREADS_X, a.smem_bytes, e->stream>>>(a);
+        else if (fulls && force_base()) {                   // tuning: the partial-suite kernel (seven warps, pipelined roles) on the full suite
+            deal_base_slots(a);
+            suite_fused_kernel<false, false, true><<<grid, CTA_THREADS, a.smem_bytes, e->stream>>>(a);
+        }
         else if (fulls) suite_fused_kernel<true, false><<<grid, CTA_THREADS, fulls_smem(a.smem_bytes), e->stream>>>(a);
         else if (!(a.gmask & ~(unsigned)G_ALL) && !fastk) {
             deal_base_slots(a);

@@ -72,10 +72,11 @@ def test_suite_block_boundaries(pq, n_symbols):
     _run_vs_oracle(pq, d)
 
 
-@pytest.mark.parametrize("n_symbols", [4736, 5100, 5300, 5500])
+@pytest.mark.parametrize("n_symbols", [4736, 5100, 5300, 5500, 6272, 7850, 7900, 9472])
 def test_suite_around_one_block_per_sm(pq, n_symbols):
-    """148 SMs: 148 blocks (nine-warp small-panel variant), 160 (same + tail CTAs of one role each), 166 (plain kernel +
-    7-role tail CTAs), 172 (plain, no tail spreading) -- every launch shape of launch_suite against the oracle, all symbols."""
+    """148 SMs: 148 blocks (nine-warp small-panel variant), 160 / 166 / 172 / 196 (one GPU's share of config 4 at 8 GPUs) /
+    246 blocks (the same + the blocks beyond one per SM as compact tail CTAs on a second stream: three role warps + a producer
+    each), 247 and 296 blocks (the plain kernel) -- every launch shape of launch_suite against the oracle, all symbols."""
     d = synth.ohlcv(n_symbols, 200, seed=900 + n_symbols)
     _run_vs_oracle(pq, d)
 
