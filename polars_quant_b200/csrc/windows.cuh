@@ -53,6 +53,7 @@ struct WinArgs {
     int smem_bytes[W_MAX_GROUPS];
     int n_groups;
     int ns;                            // stages of the input ring (2 .. NS)
+    int relaxed_wait;                  // sleep between failed tries of the stage wait
     int steady_lead;                   // a lane is past every warm-up once t - start >= steady_lead
     int n_symbols, n_bars, n_blocks, bars_padded;
 };
@@ -384,7 +385,8 @@ __device__ __forceinline__ void run_unit(UNIT &R, const WinArgs &A, const WinUni
     };
     for (int it = 0; it < n_iter; ++it) {
         const int st = it % ns;
-        mbar_wait(full + st * 8, (it / ns) & 1);
+        if (A.relaxed_wait) mbar_wait_relaxed(full + st * 8, (it / ns) & 1);
+        else mbar_wait(full + st * 8, (it / ns) & 1);
         const uint32_t sp = st * W_STAGE_BYTES + src_lane * 8;
         const int t0 = it * SB;
         if (t0 >= steady_from && t0 + SB <= A.n_bars) {

@@ -166,6 +166,27 @@ def test_candle_functions_through_the_polars_plugin_symbols(g):
         plugin.call("bop", [o, hn, l, c])                               # momentum.rs:119
 
 
+def test_every_pattern_through_the_reference_shim_names(g):
+    """polars_quant_b200.talib carries the reference's 61 CDL* names (+ AVGPRICE / MEDPRICE / TYPPRICE / WCLPRICE / BOP) with the
+    reference's signatures: every one of them, called like the reference's shim, gives the golden column."""
+    import pyarrow as pa
+    from polars_quant_b200 import talib
+    names = [str(n) for n in g["names"]]
+    pen_names = [str(x) for x in g["penetration_names"]]
+    s = 7
+    o, h, l, c = (pa.array(g[k][s]) for k in ("open", "high", "low", "close"))
+    for k, n in enumerate(names):
+        f = getattr(talib, n.upper())
+        out = f(o, h, l, c)
+        assert out.type == pa.int32() and np.array_equal(out.to_numpy(), g["patterns"][k][s]), n
+        if n in pen_names:
+            out = f(o, h, l, c, penetration=float(g["penetration_value"]))
+            assert np.array_equal(out.to_numpy(), g["patterns_pen"][pen_names.index(n)][s]), n
+    for k, out in enumerate((talib.AVGPRICE(o, h, l, c), talib.MEDPRICE(h, l), talib.TYPPRICE(h, l, c), talib.WCLPRICE(h, l, c),
+                             talib.BOP(o, h, l, c))):
+        assert np.array_equal(out.to_numpy().view(np.uint64), g["prices"][k][s].view(np.uint64)), k
+
+
 def test_config2_size_panels_against_the_c_oracle():
     """Beyond the golden panel: full BASELINE config-2 shape (5,000 x 2,520) of random-walk OHLC and of the busy
     synthetic candles, every pattern column and price output against oracle/pq_candles.c, bit for bit."""
