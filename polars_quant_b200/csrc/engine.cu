@@ -94,7 +94,7 @@ struct pqb_engine {
     cudaStream_t stream = nullptr;       // compute
     cudaStream_t h2d = nullptr, d2h = nullptr;
     cudaStream_t aux = nullptr;          // the compact tail launch of a small panel runs beside the main launch (launch_suite)
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_pre = nullptr;
     void *flush_buf = nullptr;
     size_t flush_bytes = 0;
     std::mutex mu;                       // guards the single-column scratch panel
@@ -241,6 +241,17 @@ struct pqb_panel {
     uint32_t *d_vmask = nullptr;                        // tiled [block][bar][4]
     uint32_t *d_ovm[PQB_N_OUTPUTS] = {};                // tiled [block][bar] per output
     uint8_t *d_flags = nullptr;
+    // symbol compaction (prepare_nulls / launch_suite): the flagged symbols of a device-resident panel copied into blocks of
+    // their own.  x slot i holds symbol h_symmap[i].
+    bool compact = false;                               // the structures below describe the panel's current columns
+    int64_t n_x = 0, n_xblocks = 0, x_cap_blocks = 0;   // flagged symbols, their blocks, blocks allocated
+    std::vector<int32_t> h_symmap, h_xstart;            // x slot -> symbol (-1: empty); explicit starts of the slots
+    std::vector<uint8_t> h_xflags;
+    std::vector<int32_t> h_start_c;                     // starts by the plain rule for EVERY symbol (the plain kernel runs all blocks)
+    int *d_symmap = nullptr, *d_xstart = nullptr, *d_start_c = nullptr;
+    uint8_t *d_xflags = nullptr;
+    double *x_in[PQB_N_FIELDS] = {}, *x_out[PQB_N_OUTPUTS] = {};
+    uint32_t *x_vmask = nullptr, *x_ovm[PQB_N_OUTPUTS] = {};
     // crossover signals (signals_host.inc): row-major int8 planes, allocated on first use
     int8_t *d_sig = nullptr, *h_sig = nullptr;
     bool inputs_resident = false;        // the tiled input planes hold the panel (upload / run_host / fill_synthetic)
@@ -278,9 +289,15 @@ extern "C" int pqb_engine_create(int device, pqb_engine **out) {
     CU(cudaSetDevice(device));
     CU(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&e->h2d, cudaStreamNonBlocking));
-    CU(cudaStreamCreateWithFlags(&e->aux, cudaStreamNonBlocking));
+    {   // the second stream carries the short side launches that must START beside a grid-filling main launch (compact tail CTAs,
+        // the null-aware kernel over compacted blocks): highest priority, so that their CTAs are placed first
+        int least = 0, greatest = 0;
+        CU(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+        CU(cudaStreamCreateWithPriority(&e->aux, cudaStreamNonBlocking, greatest));
+    }
     CU(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&e->ev_pre, cudaEventDisableTiming));
     CU(cudaStreamCreateWithFlags(&e->d2h, cudaStreamNonBlocking));
     CU(cudaFuncSetAttribute(suite_fused_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
     CU(cudaFuncSetAttribute(suite_fused_kernel<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
@@ -308,6 +325,7 @@ static void engine_free(pqb_engine *e) {
     if (e->aux) cudaStreamDestroy(e->aux);
     if (e->ev_fork) cudaEventDestroy(e->ev_fork);
     if (e->ev_join) cudaEventDestroy(e->ev_join);
+    if (e->ev_pre) cudaEventDestroy(e->ev_pre);
     if (e->d2h) cudaStreamDestroy(e->d2h);
     delete e;
 }
@@ -447,6 +465,14 @@ extern "C" void pqb_panel_destroy(pqb_panel *p) {
     if (p->d_vmask) cudaFree(p->d_vmask);
     if (p->d_flags) cudaFree(p->d_flags);
     if (p->d_blist) cudaFree(p->d_blist);
+    for (auto &q : p->x_in) if (q) cudaFree(q);
+    for (auto &q : p->x_out) if (q) cudaFree(q);
+    for (auto &q : p->x_ovm) if (q) cudaFree(q);
+    if (p->x_vmask) cudaFree(p->x_vmask);
+    if (p->d_symmap) cudaFree(p->d_symmap);
+    if (p->d_xstart) cudaFree(p->d_xstart);
+    if (p->d_start_c) cudaFree(p->d_start_c);
+    if (p->d_xflags) cudaFree(p->d_xflags);
     if (p->d_sig) cudaFree(p->d_sig);
     if (p->d_info) cudaFree(p->d_info);
     if (p->d_info_valid) cudaFree(p->d_info_valid);
@@ -517,6 +543,87 @@ extern "C" int pqb_panel_set_starts(pqb_panel *p, const int32_t *starts) {
     return PQB_OK;
 }
 
+// Symbol compaction (whole-panel prepare only, i.e. the device-resident path).  Per-block dispatch sends every block that
+// holds ONE flagged symbol through the null-aware kernel, whose walk is ~3x longer per bar than the plain kernel's and whose
+// CTAs are twice as heavy: 500 halted symbols spread over a 50,000-symbol panel flag 430 of its 1,563 blocks.  When the
+// flagged symbols are few, they are copied into blocks of their own instead (compact_kernel<true>), the null-aware kernel
+// walks those ceil(n / 32) blocks on the engine's second stream, the plain kernel runs EVERY original block beside it (the
+// flagged symbols' lanes compute on benign values and are overwritten afterwards: compact_kernel<false>, unpack of the
+// compacted validity words), and nothing else changes -- same kernels, same arithmetic, same bits.
+static bool compaction_enabled() {
+    static const bool v = !getenv("PQB_COMPACT_NULLS") || atoi(getenv("PQB_COMPACT_NULLS")) != 0;
+    return v;
+}
+static int prepare_compaction(pqb_panel *p, cudaStream_t st) {
+    if (!compaction_enabled() || !p->nulls_mode) return PQB_OK;
+    // flagged symbols: an interior / trailing null, or fields starting at different rows
+    std::vector<int32_t> &map = p->h_symmap;
+    map.clear();
+    p->h_start_c.assign((size_t)p->n_symbols, 0);
+    for (int64_t s = 0; s < p->n_symbols; ++s) {
+        bool flagged = p->h_flags[(size_t)s] != 0;
+        int32_t lead = -2, a = p->h_start_explicit[(size_t)s];
+        for (int f = 0; f < PQB_N_FIELDS; ++f) {
+            if (!p->d_in[f] || p->h_lead[f][(size_t)s] < 0) continue;
+            if (lead == -2) lead = p->h_lead[f][(size_t)s];
+            else if (lead != p->h_lead[f][(size_t)s]) flagged = true;
+            a = std::max(a, p->h_lead[f][(size_t)s]);
+        }
+        p->h_start_c[(size_t)s] = a;
+        if (flagged) map.push_back((int32_t)s);
+    }
+    const int64_t n_x = (int64_t)map.size(), n_xb = (n_x + SYM - 1) / SYM;
+    // worth it only while the compacted blocks are few next to the blocks they replace and next to the SMs
+    // worth it while the compacted blocks are few next to the blocks they replace, fit the GPU beside the plain launch (two
+    // null-aware CTAs per SM) and the write-back of their lanes (~3.6 us per symbol: 21 planes of 8-byte pieces) stays small
+    if (n_x == 0 || n_xb * 2 > p->n_null_blocks || n_xb > 2 * p->e->sm_count || n_x * 8 > p->n_symbols) return PQB_OK;
+    map.resize((size_t)(n_xb * SYM), -1);
+    p->h_xstart.assign(map.size(), 0);
+    p->h_xflags.assign(map.size(), 0);
+    for (size_t i = 0; i < map.size(); ++i)
+        if (map[i] >= 0) { p->h_xstart[i] = p->h_start_explicit[(size_t)map[i]]; p->h_xflags[i] = p->h_flags[(size_t)map[i]]; }
+    if (n_xb > p->x_cap_blocks) {                       // (re)allocate the compacted planes
+        for (auto &q : p->x_in) if (q) { cudaFree(q); q = nullptr; }
+        for (auto &q : p->x_out) if (q) { cudaFree(q); q = nullptr; }
+        for (auto &q : p->x_ovm) if (q) { cudaFree(q); q = nullptr; }
+        if (p->x_vmask) { cudaFree(p->x_vmask); p->x_vmask = nullptr; }
+        if (p->d_symmap) { cudaFree(p->d_symmap); p->d_symmap = nullptr; }
+        if (p->d_xstart) { cudaFree(p->d_xstart); p->d_xstart = nullptr; }
+        if (p->d_xflags) { cudaFree(p->d_xflags); p->d_xflags = nullptr; }
+        const int64_t cap = n_xb + n_xb / 4 + 1;
+        const size_t xplane = (size_t)cap * p->bars_padded * SYM * sizeof(double), xwords = (size_t)cap * p->bars_padded;
+        for (int f = 0; f < PQB_N_FIELDS; ++f) if (p->d_in[f]) CU(cudaMalloc(&p->x_in[f], xplane));
+        for (int k = 0; k < PQB_N_OUTPUTS; ++k)
+            if (p->d_out[k]) { CU(cudaMalloc(&p->x_out[k], xplane)); CU(cudaMalloc(&p->x_ovm[k], xwords * sizeof(uint32_t))); }
+        CU(cudaMalloc(&p->x_vmask, xwords * N_IN * sizeof(uint32_t)));
+        CU(cudaMalloc(&p->d_symmap, (size_t)cap * SYM * sizeof(int)));
+        CU(cudaMalloc(&p->d_xstart, (size_t)cap * SYM * sizeof(int)));
+        CU(cudaMalloc(&p->d_xflags, (size_t)cap * SYM));
+        p->x_cap_blocks = cap;
+    }
+    if (!p->d_start_c) CU(cudaMalloc(&p->d_start_c, (size_t)p->n_blocks * SYM * sizeof(int)));
+    CU(cudaMemcpyAsync(p->d_symmap, map.data(), map.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(p->d_xstart, p->h_xstart.data(), map.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(p->d_xflags, p->h_xflags.data(), map.size(), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(p->d_start_c, p->h_start_c.data(), (size_t)p->n_symbols * sizeof(int), cudaMemcpyHostToDevice, st));
+    // the compacted blocks' input validity words, from the flagged symbols' own row bitmaps
+    MaskArgs V{};
+    for (int f = 0; f < PQB_N_FIELDS; ++f) V.rm[f] = p->h_vin[f].empty() ? nullptr : p->d_vin[f];
+    V.tiled_out = p->x_vmask;
+    V.start = p->d_xstart;
+    V.symmap = p->d_symmap;
+    V.n_symbols = (int)p->n_symbols; V.n_bars = (int)p->n_bars; V.bars_padded = (int)p->bars_padded;
+    V.words_per_row = (int)p->words_per_row; V.n_blocks = (int)n_xb;
+    V.block0 = 0; V.blist = nullptr;
+    dim3 grid((unsigned)((p->bars_padded + 31) / 32), (unsigned)n_xb);
+    pack_mask_kernel<<<grid, 32, 0, st>>>(V);
+    CU(cudaGetLastError());
+    p->n_x = n_x;
+    p->n_xblocks = n_xb;
+    p->compact = true;
+    return PQB_OK;
+}
+
 // Per symbol block of the range [s0, s0 + ns) (s0 a multiple of 32): plain (every symbol valid on [start, n_bars), all
 // fields alike -> the plain kernels, leading nulls folded into `start`) or null-aware (some symbol of the block has an
 // interior / trailing null, or fields starting at different rows -> per-bar validity words, the null-aware kernel).
@@ -552,6 +659,7 @@ static int prepare_nulls(pqb_panel *p, cudaStream_t st, int64_t s0 = 0, int64_t 
         }
     }
     p->nulls_mode = p->n_null_blocks > 0;
+    p->compact = false;
     CU(cudaMemcpyAsync(p->d_start + s0, p->h_start.data() + s0, (size_t)ns * sizeof(int), cudaMemcpyHostToDevice, st));
     if (!any_null) return PQB_OK;
     const size_t bplane = (size_t)p->n_symbols * p->words_per_row * sizeof(uint32_t);
@@ -577,6 +685,7 @@ static int prepare_nulls(pqb_panel *p, cudaStream_t st, int64_t s0 = 0, int64_t 
     dim3 grid((unsigned)((p->bars_padded + 31) / 32), (unsigned)(b1 - b0));
     pack_mask_kernel<<<grid, 32, 0, st>>>(V);
     CU(cudaGetLastError());
+    if (s0 == 0 && ns == p->n_symbols) return prepare_compaction(p, st);
     return PQB_OK;
 }
 
@@ -1131,6 +1240,7 @@ static int launch_suite(pqb_panel *p, const Built &full, int64_t b0, int64_t nb,
                         int *launches) {
     pqb_engine *e = p->e;
     int n_launch = 0;
+    bool did_compact = false;
     const uint64_t stored = outputs_of_groups(full.a.gmask) | (full.a.don_fold ? 3ull << 41 : 0);
     const size_t boff = (size_t)b0 * p->bars_padded * SYM, bn = (size_t)nb * p->bars_padded * SYM;
     for (int k = 0; k < PQB_N_OUTPUTS; ++k) {
@@ -1245,6 +1355,55 @@ static int launch_suite(pqb_panel *p, const Built &full, int64_t b0, int64_t nb,
             return fail(PQB_ERR_UNSUPPORTED, "midpoint / adosc / mom / roc / cmo / mfi / cci / ... are not built for panels with "
                                              "interior nulls yet (momentum.rs functions fail on such input in the reference)");
         const int *plain_list = nullptr, *null_list = nullptr;
+        did_compact = p->compact && n_null && !go && b0 == 0 && nb == p->n_blocks;
+        if (did_compact) {
+            // ---- symbol compaction: flagged symbols -> blocks of their own (null-aware kernel, second stream) while the plain
+            //      kernel runs every original block; the flagged lanes are overwritten afterwards ----
+            const int64_t n_xb = p->n_xblocks;
+            CompactArgs G{};
+            for (int f = 0; f < PQB_N_FIELDS; ++f)
+                if (p->d_in[f] && p->x_in[f]) { G.src[G.n_planes] = p->d_in[f]; G.dst[G.n_planes] = p->x_in[f]; ++G.n_planes; }
+            G.symmap = p->d_symmap; G.bars_padded = (int)p->bars_padded; G.n_slots = (int)(n_xb * SYM);
+            compact_kernel<true><<<dim3((unsigned)(n_xb * SYM), (unsigned)((G.n_planes + 7) / 8)), 256, 0, e->stream>>>(G);
+            CU(cudaGetLastError());
+            ++n_launch;
+            // (the plain launch below waits for an event recorded on the second stream right before the null-aware kernel: both
+            // become eligible together, and the null-aware CTAs -- a ~6 ms walk -- must be placed before the plain grid fills the GPU)
+            CU(cudaEventRecord(e->ev_fork, e->stream));
+            CU(cudaStreamWaitEvent(e->aux, e->ev_fork, 0));
+            CU(cudaEventRecord(e->ev_pre, e->aux));
+            SuiteArgs an = full.a;
+            an.start = nullptr;
+            an.vmask = p->x_vmask;
+            an.symflags = p->d_xflags;
+            for (int f = 0; f < PQB_N_FIELDS; ++f) an.in[f] = p->x_in[f];
+            for (int k = 0; k < PQB_N_OUTPUTS; ++k) { an.ovm[k] = p->x_ovm[k]; an.out[k] = full.a.out[k] ? p->x_out[k] : nullptr; }
+            an.n_symbols = (int)p->n_x; an.n_blocks = (int)n_xb; an.block0 = 0; an.blist = nullptr;
+            an.split_from = -1; an.split_parts = N_ROLES; an.split_compact = 0; an.dbg = nullptr;
+            if (!an.smem_bytes && (rc = layout_rings(an, p))) return rc;
+            derive_roles(an);
+            suite_fused_kernel<false, true><<<(unsigned)n_xb, CTA_THREADS, an.smem_bytes, e->aux>>>(an);
+            CU(cudaGetLastError());
+            ++n_launch;
+            CU(cudaEventRecord(e->ev_join, e->aux));
+            SuiteArgs ap = full.a;
+            ap.start = p->d_start_c;
+            static const int order = getenv("PQB_COMPACT_ORDER") ? atoi(getenv("PQB_COMPACT_ORDER")) : 0;
+            if (order == 0) CU(cudaStreamWaitEvent(e->stream, e->ev_pre, 0));
+            if (order == 2) CU(cudaStreamWaitEvent(e->stream, e->ev_join, 0));      // (tuning: no overlap at all)
+            if ((rc = launch_one(ap, nullptr, nb))) return rc;
+            CU(cudaStreamWaitEvent(e->stream, e->ev_join, 0));
+            CompactArgs Sc{};
+            for (int k = 0; k < PQB_N_OUTPUTS; ++k)
+                if (full.a.out[k] && p->x_out[k] && (stored >> k & 1)) {
+                    if (Sc.n_planes == N_OUT) break;
+                    Sc.src[Sc.n_planes] = p->x_out[k]; Sc.dst[Sc.n_planes] = full.a.out[k]; ++Sc.n_planes;
+                }
+            Sc.symmap = p->d_symmap; Sc.bars_padded = (int)p->bars_padded; Sc.n_slots = (int)(n_xb * SYM);
+            compact_kernel<false><<<dim3((unsigned)(n_xb * SYM), (unsigned)((Sc.n_planes + 7) / 8)), 256, 0, e->stream>>>(Sc);
+            CU(cudaGetLastError());
+            ++n_launch;
+        } else
         if (n_null && n_null < nb) {
             if (!p->d_blist) CU(cudaMalloc(&p->d_blist, (size_t)p->n_blocks * 2 * sizeof(int)));
             if (p->h_blist.empty()) p->h_blist.assign((size_t)p->n_blocks * 2, 0);
@@ -1258,7 +1417,7 @@ static int launch_suite(pqb_panel *p, const Built &full, int64_t b0, int64_t nb,
             plain_list = p->d_blist + b0;
             null_list = p->d_blist + p->n_blocks + b0;
         }
-        if (n_null < nb) {                                    // the plain blocks
+        if (!did_compact && n_null < nb) {                    // the plain blocks
             const int64_t nl = nb - n_null;
             if (gb && go && split_launch_enabled()) {
                 SuiteArgs ab = full.a, ao = full.a;
@@ -1269,7 +1428,7 @@ static int launch_suite(pqb_panel *p, const Built &full, int64_t b0, int64_t nb,
                 if ((rc = launch_one(ao, plain_list, nl))) return rc;
             } else if ((rc = launch_one(full.a, plain_list, nl))) return rc;
         }
-        if (n_null) {                                         // the flagged blocks: one null-aware launch
+        if (!did_compact && n_null) {                         // the flagged blocks: one null-aware launch
             SuiteArgs an = null_variant(p, full.a);
             if (!an.smem_bytes && (rc = layout_rings(an, p))) return rc;
             if ((rc = launch_one(an, null_list, n_null))) return rc;
@@ -1288,7 +1447,7 @@ static int launch_suite(pqb_panel *p, const Built &full, int64_t b0, int64_t nb,
     if (ev_after_fused) CU(cudaEventRecord(ev_after_fused, e->stream));
     const int64_t s0 = b0 * SYM, ns = std::min<int64_t>(nb * SYM, p->n_symbols - s0);
     int64_t n_null = 0;
-    if (p->nulls_mode)
+    if (p->nulls_mode && !did_compact)
         for (int64_t b = b0; b < b0 + nb; ++b) n_null += p->h_blk_null[(size_t)b];
     // validity words written by a kernel -> Arrow bitmaps: outputs [k0, N) of the blocks `list` (or of the whole range)
     auto unpack_masks = [&](int k0, const int *list, int64_t nl, bool clear_unstored) -> int {
@@ -1332,7 +1491,7 @@ static int launch_suite(pqb_panel *p, const Built &full, int64_t b0, int64_t nb,
         V.lead[k] = full.lead[k];
         any |= V.bits[k] != nullptr;
     }
-    V.start = full.a.start ? full.a.start + s0 : nullptr;
+    V.start = did_compact ? p->d_start_c : full.a.start ? full.a.start + s0 : nullptr;
     V.n_symbols = (int)ns;
     V.n_bars = full.a.n_bars;
     V.words_per_row = (int)p->words_per_row;
@@ -1347,6 +1506,22 @@ static int launch_suite(pqb_panel *p, const Built &full, int64_t b0, int64_t nb,
         // mixed range: the flagged blocks' bitmaps come from the null-aware kernel's words (overwriting the lead-based ones)
         int rc = unpack_masks(0, p->d_blist + p->n_blocks + b0, n_null, false);
         if (rc) return rc;
+    }
+    if (did_compact) {
+        // the flagged symbols' bitmaps from the compacted blocks' validity words, row by row through the slot -> symbol map
+        MaskArgs M{};
+        int n = 0;
+        for (int k = 0; k < PQB_N_OUTPUTS; ++k)
+            if (full.a.out[k] && p->d_bits[k] && p->x_ovm[k] && (stored >> k & 1)) { M.tiled_in[n] = p->x_ovm[k]; M.rm_out[n] = p->d_bits[k]; ++n; }
+        if (n) {
+            M.n_planes = n; M.n_symbols = (int)p->n_symbols; M.n_bars = (int)p->n_bars; M.bars_padded = (int)p->bars_padded;
+            M.words_per_row = (int)p->words_per_row; M.n_blocks = (int)p->n_xblocks; M.block0 = 0; M.blist = nullptr;
+            M.symmap = p->d_symmap;
+            dim3 grid((unsigned)p->words_per_row, (unsigned)p->n_xblocks);
+            unpack_mask_kernel<<<grid, 32, 0, e->stream>>>(M);
+            CU(cudaGetLastError());
+            ++n_launch;
+        }
     }
     if (launches) *launches = n_launch;
     return PQB_OK;

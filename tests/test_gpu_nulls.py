@@ -51,6 +51,46 @@ def _null_masks(S, N, seed, frac=0.03):
     return ok
 
 
+def _check_symbol_against_the_oracle(res, s, d, ok, N):
+    c, h, l, v = (d[f] for f in F)
+    kc, kh, kl, kv = (ok[f] for f in F)
+    _check("sma", res, s, pqo.sma(c[s], 30, kc[s]))
+    _check("ema", res, s, pqo.ema(c[s], 30, kc[s]))
+    _check("tema", res, s, pqo.tema(c[s], 30, kc[s]))
+    _check("trima", res, s, pqo.trima(c[s], 30, kc[s]))
+    for name, ref in zip(("bb_upper", "bb_middle", "bb_lower"), pqo.bbands(c[s], 20, 2.0, 2.0, kc[s])):
+        _check(name, res, s, ref)
+    _check("trange", res, s, pqo.trange(h[s], l[s], c[s], kh[s], kl[s], kc[s]))
+    _check("atr", res, s, pqo.atr(h[s], l[s], c[s], 14, kh[s], kl[s], kc[s]))
+    _check("natr", res, s, pqo.natr(h[s], l[s], c[s], 14, kh[s], kl[s], kc[s]))
+    _check("obv", res, s, pqo.obv(c[s], v[s], kc[s], kv[s]))
+    _check("ad", res, s, pqo.ad(h[s], l[s], c[s], v[s], kh[s], kl[s], kc[s], kv[s]))
+    sk, sd = pqo.stoch(h[s], l[s], c[s], 9, 3, 0, 3, 0, kh[s], kl[s], kc[s])
+    _check("kdj_k", res, s, sk)
+    _check("kdj_d", res, s, sd)
+    jok = sk[1] & sd[1]
+    _check("kdj_j", res, s, (np.where(jok, 3.0 * sk[0] - 2.0 * sd[0], np.nan), jok))
+    # momentum.rs functions / midprice: the reference fails on interior or trailing nulls
+    lead_only = {f: (not ok[f][s].all()) and ok[f][s][np.argmax(ok[f][s]):].all() for f in F}
+    clean = {f: ok[f][s].all() or lead_only[f] for f in F}
+    a = int(np.argmax(kc[s]))
+    if clean["close"]:
+        for name, ref in zip(("macd", "macd_signal", "macd_hist"), pqo.macd(c[s, a:], 12, 26, 9)):
+            full_v = np.full(N, np.nan); full_k = np.zeros(N, bool)
+            full_v[a:], full_k[a:] = ref
+            _check(name, res, s, (full_v, full_k))
+        rv, rk = pqo.rsi(c[s, a:], 14)
+        full_v = np.full(N, np.nan); full_k = np.zeros(N, bool); full_v[a:], full_k[a:] = rv, rk
+        _check("rsi", res, s, (full_v, full_k))
+    else:
+        for name in ("macd", "macd_signal", "macd_hist", "rsi"):
+            assert not res[name][1][s].any(), f"{name} symbol {s}: reference fails on nulls -> all null"
+    if not (clean["close"] and clean["high"] and clean["low"]):
+        assert not res["willr"][1][s].any()
+    if not (clean["high"] and clean["low"]):
+        assert not res["midprice"][1][s].any()
+
+
 def test_null_semantics_function_by_function(pq=None):
     import polars_quant_b200 as pq
     S, N = 40, 700
@@ -61,41 +101,7 @@ def test_null_semantics_function_by_function(pq=None):
     c, h, l, v = (d[f] for f in F)
     kc, kh, kl, kv = (ok[f] for f in F)
     for s in range(S):
-        _check("sma", res, s, pqo.sma(c[s], 30, kc[s]))
-        _check("ema", res, s, pqo.ema(c[s], 30, kc[s]))
-        _check("tema", res, s, pqo.tema(c[s], 30, kc[s]))
-        _check("trima", res, s, pqo.trima(c[s], 30, kc[s]))
-        for name, ref in zip(("bb_upper", "bb_middle", "bb_lower"), pqo.bbands(c[s], 20, 2.0, 2.0, kc[s])):
-            _check(name, res, s, ref)
-        _check("trange", res, s, pqo.trange(h[s], l[s], c[s], kh[s], kl[s], kc[s]))
-        _check("atr", res, s, pqo.atr(h[s], l[s], c[s], 14, kh[s], kl[s], kc[s]))
-        _check("natr", res, s, pqo.natr(h[s], l[s], c[s], 14, kh[s], kl[s], kc[s]))
-        _check("obv", res, s, pqo.obv(c[s], v[s], kc[s], kv[s]))
-        _check("ad", res, s, pqo.ad(h[s], l[s], c[s], v[s], kh[s], kl[s], kc[s], kv[s]))
-        sk, sd = pqo.stoch(h[s], l[s], c[s], 9, 3, 0, 3, 0, kh[s], kl[s], kc[s])
-        _check("kdj_k", res, s, sk)
-        _check("kdj_d", res, s, sd)
-        jok = sk[1] & sd[1]
-        _check("kdj_j", res, s, (np.where(jok, 3.0 * sk[0] - 2.0 * sd[0], np.nan), jok))
-        # momentum.rs functions / midprice: the reference fails on interior or trailing nulls
-        lead_only = {f: (not ok[f][s].all()) and ok[f][s][np.argmax(ok[f][s]):].all() for f in F}
-        clean = {f: ok[f][s].all() or lead_only[f] for f in F}
-        a = int(np.argmax(kc[s]))
-        if clean["close"]:
-            for name, ref in zip(("macd", "macd_signal", "macd_hist"), pqo.macd(c[s, a:], 12, 26, 9)):
-                full_v = np.full(N, np.nan); full_k = np.zeros(N, bool)
-                full_v[a:], full_k[a:] = ref
-                _check(name, res, s, (full_v, full_k))
-            rv, rk = pqo.rsi(c[s, a:], 14)
-            full_v = np.full(N, np.nan); full_k = np.zeros(N, bool); full_v[a:], full_k[a:] = rv, rk
-            _check("rsi", res, s, (full_v, full_k))
-        else:
-            for name in ("macd", "macd_signal", "macd_hist", "rsi"):
-                assert not res[name][1][s].any(), f"{name} symbol {s}: reference fails on nulls -> all null"
-        if not (clean["close"] and clean["high"] and clean["low"]):
-            assert not res["willr"][1][s].any()
-        if not (clean["high"] and clean["low"]):
-            assert not res["midprice"][1][s].any()
+        _check_symbol_against_the_oracle(res, s, d, ok, N)
     # symbols without interior nulls and with one common start are exactly the trimmed series
     for s in (0, 5):
         a = int(np.argmax(kc[s]))
@@ -170,3 +176,43 @@ def test_single_column_calls_with_nulls():
     # and a clean call right after a null-aware one (scratch panel state is reset)
     N.check(L.pqb_sma(eng._h, C.byref(col(c)), 10, C.byref(oc)))
     assert T.compare("sma", *got(), *pqo.sma(c, 10))[0] == 0
+
+
+def test_symbol_compaction_few_flagged_symbols_in_a_large_panel():
+    """A device-resident panel in which FEW symbols need the null-aware kernel (halts, a delisting, a field that starts late)
+    and they are spread over many blocks: the engine copies them into blocks of their own, runs the null-aware kernel on those
+    beside the plain kernel on every original block, and writes their lanes back (engine.cu "symbol compaction").  Every output
+    of every flagged symbol and of its block neighbours against the oracle; the whole panel against the chunked host pipeline,
+    which never compacts (per-block dispatch), bit for bit."""
+    import polars_quant_b200 as pq
+    S, N = 1500, 520
+    d = synth.ohlcv(S, N, seed=77)
+    ok = {f: np.ones((S, N), bool) for f in F}
+    rng = np.random.default_rng(3)
+    lead = rng.integers(0, 40, S)
+    for s in range(S):
+        if s % 7 == 0:
+            for f in F:
+                ok[f][s, :lead[s]] = False                    # later listings: leading nulls shared by the fields (plain path)
+    flagged = [5, 70, 131, 200, 333, 334, 470, 512, 777, 900, 1023, 1250, 1499]
+    for i, s in enumerate(flagged):
+        kind = i % 5
+        if kind == 0: ok["close"][s, 200:203] = False         # a halt in close
+        elif kind == 1:
+            for f in F: ok[f][s, N - 60:] = False             # delisted
+        elif kind == 2: ok["volume"][s, :33] = False          # volume starts later than the other fields
+        elif kind == 3: ok["high"][s, 301] = False            # one missing high
+        else:
+            for f in F: ok[f][s, 100:140] = False             # a long halt in every field
+    panel = _panel_with_nulls(pq, d, ok)
+    res = panel.compute()
+    for s in sorted(set(flagged + [4, 6, 69, 71, 332, 335, 1498, 0, 1, 7, 14])):
+        _check_symbol_against_the_oracle(res, s, d, ok, N)
+    got = {k: (v[0].copy(), v[1].copy()) for k, v in res.items()}
+    panel.run_host(chunk_symbols=32)                          # one launch per 32-symbol chunk: per-block dispatch, no compaction
+    ref = panel.outputs()
+    for name in pqo.OUTPUT_NAMES:
+        assert np.array_equal(got[name][1], ref[name][1]), name
+        m = ref[name][1]
+        assert np.array_equal(got[name][0][m].view(np.uint64), ref[name][0][m].view(np.uint64)), name
+    panel.close()
