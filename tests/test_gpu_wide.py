@@ -79,6 +79,29 @@ def test_lazy_result_columns_are_the_table_columns(tmp_path):
         lazy["S_0_rsi"]
 
 
+def test_wide_suite_sharded_over_devices_equals_one_device(tmp_path):
+    """`WidePanel.suite(devices=[...])`: the symbols sharded over GPUs (contiguous whole-block ranges, one host thread each; the
+    same device twice on a one-GPU box) give the table of one device, eagerly and lazily."""
+    n_dev = max(1, N.lib().pqb_device_count())
+    devices = list(range(n_dev)) if n_dev > 1 else [0, 0]
+    for k in range(70):                                        # three symbol blocks: shards of 32 + 38 symbols on two devices
+        days = range(k % 5, 260) if k % 9 else [d for d in range(0, 260) if d != 120]
+        pq.write_table(_symbol_table(100 + k, list(days)), tmp_path / ("T%03d.parquet" % k))
+    t = wide.load(tmp_path)
+    wp = wide.WidePanel(t)
+    names = ["ema", "bb_lower", "atr", "kdj_d"]
+    one = wp.suite(outputs=names)
+    many = wp.suite(outputs=names, devices=devices)
+    assert many.column_names == one.column_names and many.equals(one)
+    lazy = wp.suite(outputs=names, devices=devices, lazy=True)
+    assert lazy.column_names == one.column_names[1:]
+    for name in ("T000_ema", "T031_atr", "T032_kdj_d", "T069_bb_lower"):
+        assert lazy[name].equals(one[name].combine_chunks()), name
+    v, ok = lazy.matrix("atr")
+    assert v.shape == (70, 260) and np.array_equal(ok[40], ~np.asarray(one["T040_atr"].combine_chunks().is_null()))
+    assert lazy.table().equals(one)
+
+
 def test_wide_candles_and_null_refusal(tmp_path):
     pq.write_table(_symbol_table(5, list(range(0, 300))), tmp_path / "AAA.parquet")
     pq.write_table(_symbol_table(6, list(range(50, 300))), tmp_path / "BBB.parquet")
