@@ -54,6 +54,7 @@ struct WinArgs {
     int n_groups;
     int ns;                            // stages of the input ring (2 .. NS)
     int relaxed_wait;                  // sleep between failed tries of the stage wait
+    int block_major;                   // CTA order: the groups of one symbol block next to each other (they share its input rows in L2)
     int steady_lead;                   // a lane is past every warm-up once t - start >= steady_lead
     int n_symbols, n_bars, n_blocks, bars_padded;
 };
@@ -259,7 +260,7 @@ struct UnitKdj {
             den_n = hn - ln;
         }
         if (M & 2) {
-            if (!ok) fk = slow_div(pNum, den);
+            if (!ok) fk = (pNum == 0.0) ? pNum * den : slow_div(pNum, den);
             pFk = z ? pNum * copysign(pinf(), pDen) : fk;
         }
         if (M & 1) {
@@ -323,7 +324,7 @@ struct UnitWmd {
             stg(U.out[3] + X.pos, wl);
         }
         if (M & 2) {
-            if (!ok) q = slow_div(num, den);
+            if (!ok) q = (num == 0.0) ? num * den : slow_div(num, den);
             stg(U.out[0] + X.pos - SYM, z ? 0.0 : q);
         }
         if (M & 1) {
@@ -451,7 +452,8 @@ __global__ void __launch_bounds__(MAXT, MINB) window_suite_kernel(const __grid_c
     const uint32_t stage = smem_u32(smem_dyn), full = smem_u32(full_p);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     // group-major: the CTAs of the heaviest group (group 0) are scheduled first, the lighter groups fill in behind them
-    const int g = (int)(blockIdx.x / (unsigned)A.n_blocks), block = (int)(blockIdx.x % (unsigned)A.n_blocks);
+    const int g = A.block_major ? (int)(blockIdx.x % (unsigned)A.n_groups) : (int)(blockIdx.x / (unsigned)A.n_blocks);
+    const int block = A.block_major ? (int)(blockIdx.x / (unsigned)A.n_groups) : (int)(blockIdx.x % (unsigned)A.n_blocks);
     const int n_units = A.n_units[g];
     if (threadIdx.x == 0) {
 #pragma unroll
