@@ -340,7 +340,7 @@ def main():
     # pipelined with H2D || pack + fused suite + unpack || D2H) -> pqb_panel_export_arrow (all result columns as one
     # Arrow struct array over the pinned result planes) -> release.  Timed by the host clock around the calls (they
     # return after the last D2H has landed), max over ranks.
-    e2e, cpu = None, None
+    e2e, cpu, halted = None, None, None
     e2e_launches = 0
     if not args.no_e2e:
         import ctypes as C
@@ -418,6 +418,27 @@ def main():
             rate, used, reps = cpu_suite_rate(c, h, l, v, cores, args.cpu_seconds)
             cpu = {"value": rate, "unit": UNIT, "cores": used, "kind": "port",
                    "sample": f"{ns} symbols x {N} bars of the same synthetic panel, {reps} passes, C oracle (oracle/pq_oracle.c)"}
+        # ---- a realistic panel on the same staging (N = 1 only): 1 % of the symbols with a 3-bar trading halt in close,
+        #      device-resident suite (engine.cu "symbol compaction": the halted symbols run the null-aware kernel in blocks of
+        #      their own beside the plain kernel on every original block) ----
+        halted = None
+        if world == 1 and not args.no_extra:
+            try:
+                n_h = max(1, Se // 100)
+                okb = np.ones(N, dtype=bool)
+                okb[2000:2003] = False
+                bits = np.packbits(okb, bitorder="little")
+                for s_ in np.linspace(0, Se - 1, n_h).astype(int):
+                    hp.set_column(int(s_), "close", np.ascontiguousarray(mats["close"][int(s_)]), validity=bits)
+                hp.upload()
+                t_h, _, nl_h = hp.time_device(params, warmup=2, iters=5)
+                halted = {"workload": "%d x %d, %d symbols (1 %%) with a 3-bar halt in close, device-resident" % (Se, N, n_h),
+                          "kernel": "compact_kernel + suite_fused_kernel<false,true> (compacted blocks, second stream) || suite_fused_kernel<true,false> "
+                                    "+ compact_kernel + validity", "ms": t_h / 5, "launches": nl_h,
+                          "value": Se * N / (t_h / 5 * 1e-3), "unit": UNIT,
+                          "vs_clean_panel": (t_h / 5) / (ms_total / args.steps) * (S / Se)}
+            except Exception as ex:
+                halted = {"error": repr(ex)}
         del refs, _keep, mats
         hp.close()
 
@@ -484,6 +505,8 @@ def main():
         extra("c5", lambda: bench_c5(pq, NV, engine, peak))
         extra("candles", candle)
         extra("access_mix_ceiling", mix)
+        if not args.no_e2e and halted is not None:
+            other["c4_one_percent_halted_symbols"] = halted
 
     if rank == 0:
         traffic, traffic_src = traffic_record(S, N)
