@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- fused indicator suite throughput (symbol.bars/s) on B200, one JSON line.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c4|c2]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c4|c2|c3|c5]
 
 A "step" is one pass of the fused 15-indicator / 21-output suite over one synthetic random-walk
 OHLCV panel already resident in HBM.  N > 1 is launched by torchrun, one process per GPU; symbols
@@ -204,14 +204,14 @@ def traffic_record(S, N):
     return None, None
 
 
-def bench_c3(pq, NV, engine, peak, iters=5):
+def bench_c3(pq, NV, engine, peak, iters=5, warmup=2):
     """BASELINE config 3: 500 x 1,000,000, EMA(12, 26, 200, 5000) + MACD(12, 26, 9): 1 plane in, 7 out = 64 B per
     symbol-bar."""
     from polars_quant_b200 import longrows
     S, NB = 500, 1_000_000
     lp = longrows.LongPanel(S, NB, engine=engine, ema_periods=(12, 26, 200, 5000), macd=(12, 26, 9), host_staging=False)
     lp.fill_synthetic(seed=3, sigma=0.0005)
-    ms, launches = lp.time_device(warmup=2, iters=iters)
+    ms, launches = lp.time_device(warmup=warmup, iters=iters)
     lp.close()
     g = 64 * S * NB / (ms * 1e-3) / 1e9
     return {"workload": "BASELINE config 3: 500 symbols x 1,000,000 minute bars, EMA(12,26,200,5000) + MACD(12,26,9) in one pass",
@@ -219,19 +219,52 @@ def bench_c3(pq, NV, engine, peak, iters=5):
             "algorithmic_bytes_per_symbol_bar": 64, "achieved_gbs": g, "frac": g / peak}
 
 
-def bench_c5(pq, NV, engine, peak, iters=5):
+def bench_c5(pq, NV, engine, peak, iters=5, warmup=2):
     """BASELINE config 5: 10,000 x 5,040, KDJ(k) for k in 5/9/14/60/250 + WILLR / MIDPRICE / Donchian(p) for p in
     5/20/55/250 + ATR(14): 3 planes in, 28 out = 248 B per symbol-bar."""
     from polars_quant_b200 import windows
     S, NB = 10_000, 5_040
     wp = windows.WindowPanel(S, NB, engine=engine, kdj=(5, 9, 14, 60, 250), ext=(5, 20, 55, 250), atr=14, host_staging=False)
     wp.fill_synthetic(seed=55, sigma=0.02)
-    ms, launches = wp.time_device(warmup=2, iters=iters)
+    ms, launches = wp.time_device(warmup=warmup, iters=iters)
     wp.close()
     g = 248 * S * NB / (ms * 1e-3) / 1e9
     return {"workload": "BASELINE config 5: 10,000 x 5,040, KDJ(5,9,14,60,250) + WILLR/MIDPRICE/Donchian(5,20,55,250) + ATR(14)",
             "kernel": "window_suite_kernel", "launches": launches, "kernel_ms": ms, "value": S * NB / (ms * 1e-3), "unit": UNIT,
             "algorithmic_bytes_per_symbol_bar": 248, "achieved_gbs": g, "frac": g / peak}
+
+
+def run_config_3_or_5(args, rank):
+    """`--workload c3|c5`: the long-row / many-window panels as a bench line of their own (device-resident, one GPU; under
+    torchrun every rank but 0 exits).  Same timing rules: W >= 3 warm-up passes, K timed passes between CUDA events on the engine
+    stream; inputs + outputs per pass (12.5 - 32 GB) dwarf the L2."""
+    if rank != 0:
+        return
+    import polars_quant_b200 as pq
+    from polars_quant_b200 import _native as NV
+    engine = pq.get_engine(0)
+    peak, peak_src = measured_peak()
+    with ClockSampler(0) as clocks:
+        rec = (bench_c3 if args.workload == "c3" else bench_c5)(pq, NV, engine, peak, iters=max(args.steps, 1), warmup=max(args.warmup, 3))
+    S, NB = (500, 1_000_000) if args.workload == "c3" else (10_000, 5_040)
+    line = {"metric": "symbol_bars_per_sec_" + ("ema_macd_long_rows" if args.workload == "c3" else "rolling_window_suite"),
+            "value": rec["value"], "unit": UNIT, "n_gpus": 1, "steps": max(args.steps, 1), "warmup": max(args.warmup, 3),
+            "ms_per_step": rec["kernel_ms"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": {"workload": rec["workload"], "symbols": S, "bars": NB,
+                                            "l2": "inputs + outputs per pass are far larger than the 126 MB L2; no flush needed"},
+            "roofline": {"bound": "hbm", "achieved": rec["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": rec["frac"],
+                         "traffic": None, "kernel": rec["kernel"], "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": rec["algorithmic_bytes_per_symbol_bar"] * S * NB, "kernel_ms": rec["kernel_ms"]},
+            "cpu_baseline": None, "e2e": None, "gpu_launches": rec["launches"] * max(args.steps, 1), "clocks": clocks.summary()}
+    tr = ROOT / "profiles" / "traffic.json"
+    try:
+        for r in json.loads(tr.read_text()):
+            if r.get("workload") == args.workload:
+                line["roofline"]["traffic"] = r.get("dram_bytes_per_launch")
+                line["roofline"]["traffic_source"] = {k: r.get(k) for k in ("captured_at_commit", "kernel")}
+    except Exception:
+        pass
+    print(json.dumps(line), flush=True)
 
 
 def main():
@@ -240,7 +273,9 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS) + ["c3", "c5"],
+                    help="c4 (default) / c2: the fused suite; c3: EMA x 4 + MACD over 500 x 1,000,000 (LongPanel); c5: KDJ x 5 + WILLR / "
+                         "MIDPRICE / Donchian x 4 + ATR over 10,000 x 5,040 (WindowPanel) -- kernel-only lines, one GPU")
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
                     help="strong (default): the workload's symbols are sharded over the GPUs (BASELINE config 4: '50,000 x 5,040 "
                          "symbol-sharded at 1/2/4/8'); weak: every GPU runs the whole workload shape")
@@ -259,6 +294,13 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.workload in ("c3", "c5"):
+        if args.impl == "reference":
+            if rank == 0:
+                print(json.dumps({"impl": "reference", "unavailable": "the reference arm is timed on the headline workloads (c4 / c2) only"}), flush=True)
+            return
+        run_config_3_or_5(args, rank)
+        return
     S_total, N, desc = WORKLOADS[args.workload]
     if args.symbols:
         S_total = args.symbols
