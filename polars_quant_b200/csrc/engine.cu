@@ -1230,6 +1230,17 @@ static int fulls_smem(int need) {
     return ev ? std::max(need, atoi(ev)) : need;
 }
 
+// Tuning knob (PQB_COMPACT_DELAY_US, default off): one thread that sleeps ~`ns` nanoseconds on the main stream, so that the CTAs
+// of the side launch of a symbol compaction are resident before the plain grid fills every SM.
+__global__ void delay_kernel(unsigned ns) {
+    unsigned long long t0, t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    do {
+        __nanosleep(1000);
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    } while (t - t0 < ns);
+}
+
 static bool force_base() {
     static const bool v = getenv("PQB_FORCE_BASE") && atoi(getenv("PQB_FORCE_BASE")) != 0;
     return v;
@@ -1389,7 +1400,11 @@ static int launch_suite(pqb_panel *p, const Built &full, int64_t b0, int64_t nb,
             SuiteArgs ap = full.a;
             ap.start = p->d_start_c;
             static const int order = getenv("PQB_COMPACT_ORDER") ? atoi(getenv("PQB_COMPACT_ORDER")) : 0;
-            if (order == 0) CU(cudaStreamWaitEvent(e->stream, e->ev_pre, 0));
+            if (order == 0) {
+                CU(cudaStreamWaitEvent(e->stream, e->ev_pre, 0));
+                static const int delay_us = getenv("PQB_COMPACT_DELAY_US") ? atoi(getenv("PQB_COMPACT_DELAY_US")) : 0;   // (measured: profiles/r03_halted_symbols.txt -- helps a 20,000-symbol panel, hurts a 50,000-symbol one)
+                if (delay_us > 0) { delay_kernel<<<1, 32, 0, e->stream>>>((unsigned)delay_us * 1000u); CU(cudaGetLastError()); }
+            }
             if (order == 2) CU(cudaStreamWaitEvent(e->stream, e->ev_join, 0));      // (tuning: no overlap at all)
             if ((rc = launch_one(ap, nullptr, nb))) return rc;
             CU(cudaStreamWaitEvent(e->stream, e->ev_join, 0));
