@@ -1230,8 +1230,11 @@ static int fulls_smem(int need) {
     return ev ? std::max(need, atoi(ev)) : need;
 }
 
-// Tuning knob (PQB_COMPACT_DELAY_US, default off): one thread that sleeps ~`ns` nanoseconds on the main stream, so that the CTAs
-// of the side launch of a symbol compaction are resident before the plain grid fills every SM.
+// One thread that sleeps ~`ns` nanoseconds on the main stream (PQB_COMPACT_DELAY_US, default 40): the null-aware CTAs of a symbol
+// compaction are then resident -- one per SM, each asking for the SM's whole shared memory so that no plain CTA moves in beside
+// it -- before the plain grid fills the rest of the GPU.  Measured with a timeline build (globaltimer stamps, profiles/
+// r03_halted_symbols.txt): without it they only start when the first plain wave ends (2.0 ms in); sharing an SM with a plain CTA
+// their 4.2 ms walk takes 6 - 10 ms (50,000 x 5,040: last null-aware CTA done at 11.7 - 13.4 ms, after the plain launch).
 __global__ void delay_kernel(unsigned ns) {
     unsigned long long t0, t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
@@ -1393,7 +1396,10 @@ static int launch_suite(pqb_panel *p, const Built &full, int64_t b0, int64_t nb,
             an.split_from = -1; an.split_parts = N_ROLES; an.split_compact = 0; an.dbg = nullptr;
             if (!an.smem_bytes && (rc = layout_rings(an, p))) return rc;
             derive_roles(an);
-            suite_fused_kernel<false, true><<<(unsigned)n_xb, CTA_THREADS, an.smem_bytes, e->aux>>>(an);
+            // (exclusive: with the whole shared memory of an SM requested, no plain CTA can move in beside a null-aware CTA -- see
+            // below why that matters)
+            static const int exclusive = getenv("PQB_COMPACT_EXCLUSIVE") ? atoi(getenv("PQB_COMPACT_EXCLUSIVE")) : 1;
+            suite_fused_kernel<false, true><<<(unsigned)n_xb, CTA_THREADS, exclusive ? kMaxSmem : an.smem_bytes, e->aux>>>(an);
             CU(cudaGetLastError());
             ++n_launch;
             CU(cudaEventRecord(e->ev_join, e->aux));
@@ -1402,7 +1408,7 @@ static int launch_suite(pqb_panel *p, const Built &full, int64_t b0, int64_t nb,
             static const int order = getenv("PQB_COMPACT_ORDER") ? atoi(getenv("PQB_COMPACT_ORDER")) : 0;
             if (order == 0) {
                 CU(cudaStreamWaitEvent(e->stream, e->ev_pre, 0));
-                static const int delay_us = getenv("PQB_COMPACT_DELAY_US") ? atoi(getenv("PQB_COMPACT_DELAY_US")) : 0;   // (measured: profiles/r03_halted_symbols.txt -- helps a 20,000-symbol panel, hurts a 50,000-symbol one)
+                static const int delay_us = getenv("PQB_COMPACT_DELAY_US") ? atoi(getenv("PQB_COMPACT_DELAY_US")) : 40;
                 if (delay_us > 0) { delay_kernel<<<1, 32, 0, e->stream>>>((unsigned)delay_us * 1000u); CU(cudaGetLastError()); }
             }
             if (order == 2) CU(cudaStreamWaitEvent(e->stream, e->ev_join, 0));      // (tuning: no overlap at all)
