@@ -307,6 +307,8 @@ extern "C" int pqb_engine_create(int device, pqb_engine **out) {
     CU(cudaFuncSetAttribute(suite_fused_kernel<true, false, false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     CU(cudaFuncSetAttribute(suite_fused_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
     CU(cudaFuncSetAttribute(suite_fused_kernel<false, false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    CU(cudaFuncSetAttribute(suite_fused_kernel<false, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+    CU(cudaFuncSetAttribute(suite_fused_kernel<false, true, false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     CU(cudaFuncSetAttribute(suite_fused_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
     CU(cudaFuncSetAttribute(suite_fused_kernel<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     CU(cudaFuncSetAttribute(suite_fused_kernel<false, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
@@ -1399,7 +1401,11 @@ static int launch_suite(pqb_panel *p, const Built &full, int64_t b0, int64_t nb,
             // (exclusive: with the whole shared memory of an SM requested, no plain CTA can move in beside a null-aware CTA -- see
             // below why that matters)
             static const int exclusive = getenv("PQB_COMPACT_EXCLUSIVE") ? atoi(getenv("PQB_COMPACT_EXCLUSIVE")) : 1;
-            suite_fused_kernel<false, true><<<(unsigned)n_xb, CTA_THREADS, exclusive ? kMaxSmem : an.smem_bytes, e->aux>>>(an);
+            static const int split0 = getenv("PQB_COMPACT_SPLIT0") ? atoi(getenv("PQB_COMPACT_SPLIT0")) : 1;
+            if (split0 && exclusive)        // (the variant with SMA / EMA / TEMA / MACD over two warps: 288 threads, one CTA per SM)
+                suite_fused_kernel<false, true, false, true><<<(unsigned)n_xb, CTA_THREADS + 32, kMaxSmem, e->aux>>>(an);
+            else
+                suite_fused_kernel<false, true><<<(unsigned)n_xb, CTA_THREADS, exclusive ? kMaxSmem : an.smem_bytes, e->aux>>>(an);
             CU(cudaGetLastError());
             ++n_launch;
             CU(cudaEventRecord(e->ev_join, e->aux));
