@@ -578,7 +578,8 @@ static int prepare_compaction(pqb_panel *p, cudaStream_t st) {
     // worth it only while the compacted blocks are few next to the blocks they replace and next to the SMs
     // worth it while the compacted blocks are few next to the blocks they replace, fit the GPU beside the plain launch (two
     // null-aware CTAs per SM) and the write-back of their lanes (~3.6 us per symbol: 21 planes of 8-byte pieces) stays small
-    if (n_x == 0 || n_xb * 2 > p->n_null_blocks || n_xb > 2 * p->e->sm_count || n_x * 8 > p->n_symbols) return PQB_OK;
+    // (up to a third of the symbols and four rounds of null-aware CTAs in DIRECT mode, launch_suite: no write-back there)
+    if (n_x == 0 || n_xb * 2 > p->n_null_blocks || n_xb > 4 * p->e->sm_count || n_x * 3 > p->n_symbols) return PQB_OK;
     map.resize((size_t)(n_xb * SYM), -1);
     p->h_xstart.assign(map.size(), 0);
     p->h_xflags.assign(map.size(), 0);
@@ -925,6 +926,7 @@ static int build_args(const pqb_panel *p, const pqb_suite_params *sp, Built *out
     A.don_fold = 0; A.don_p = 1;
     // the arguments of the PLAIN kernels; launch_suite derives the null-aware variant (null_variant) for the symbol
     // blocks that need it
+    A.symmap = nullptr;
     A.start = p->d_start;      // (always: with pipelined intake the starts reach the device after these arguments are built)
     A.vmask = nullptr;
     A.symflags = nullptr;
@@ -1388,48 +1390,62 @@ static int launch_suite(pqb_panel *p, const Built &full, int64_t b0, int64_t nb,
             CU(cudaEventRecord(e->ev_fork, e->stream));
             CU(cudaStreamWaitEvent(e->aux, e->ev_fork, 0));
             CU(cudaEventRecord(e->ev_pre, e->aux));
+            // Two modes.  OVERLAPPED (few flagged symbols): the null-aware kernel writes compacted output planes on the second stream
+            // while the plain kernel runs, and a write-back pass (~3.6 us per symbol) puts the lanes in place.  DIRECT (many): the
+            // null-aware kernel runs AFTER the plain one on the same stream and stores straight into the symbols' own lanes
+            // (SuiteArgs::symmap), overwriting what the plain kernel left there -- no overlap, but no write-back either.
+            static const int direct_from = getenv("PQB_COMPACT_DIRECT_FROM") ? atoi(getenv("PQB_COMPACT_DIRECT_FROM")) : 1024;
+            const bool direct = p->n_x > direct_from;
             SuiteArgs an = full.a;
             an.start = nullptr;
             an.vmask = p->x_vmask;
             an.symflags = p->d_xflags;
             for (int f = 0; f < PQB_N_FIELDS; ++f) an.in[f] = p->x_in[f];
-            for (int k = 0; k < PQB_N_OUTPUTS; ++k) { an.ovm[k] = p->x_ovm[k]; an.out[k] = full.a.out[k] ? p->x_out[k] : nullptr; }
+            for (int k = 0; k < PQB_N_OUTPUTS; ++k) { an.ovm[k] = p->x_ovm[k]; an.out[k] = !full.a.out[k] ? nullptr : direct ? full.a.out[k] : p->x_out[k]; }
+            an.symmap = direct ? p->d_symmap : nullptr;
             an.n_symbols = (int)p->n_x; an.n_blocks = (int)n_xb; an.block0 = 0; an.blist = nullptr;
             an.split_from = -1; an.split_parts = N_ROLES; an.split_compact = 0; an.dbg = nullptr;
             if (!an.smem_bytes && (rc = layout_rings(an, p))) return rc;
             derive_roles(an);
-            // (exclusive: with the whole shared memory of an SM requested, no plain CTA can move in beside a null-aware CTA -- see
-            // below why that matters)
+            // (exclusive: with the whole shared memory of an SM requested, no plain CTA can move in beside a null-aware CTA)
             static const int exclusive = getenv("PQB_COMPACT_EXCLUSIVE") ? atoi(getenv("PQB_COMPACT_EXCLUSIVE")) : 1;
             static const int split0 = getenv("PQB_COMPACT_SPLIT0") ? atoi(getenv("PQB_COMPACT_SPLIT0")) : 1;
-            if (split0 && exclusive)        // (the variant with SMA / EMA / TEMA / MACD over two warps: 288 threads, one CTA per SM)
-                suite_fused_kernel<false, true, false, true><<<(unsigned)n_xb, CTA_THREADS + 32, kMaxSmem, e->aux>>>(an);
-            else
-                suite_fused_kernel<false, true><<<(unsigned)n_xb, CTA_THREADS, exclusive ? kMaxSmem : an.smem_bytes, e->aux>>>(an);
-            CU(cudaGetLastError());
-            ++n_launch;
-            CU(cudaEventRecord(e->ev_join, e->aux));
+            auto launch_null = [&](cudaStream_t st) {
+                if (split0 && exclusive)    // (the variant with SMA / EMA / TEMA / MACD over two warps: 288 threads, one CTA per SM)
+                    suite_fused_kernel<false, true, false, true><<<(unsigned)n_xb, CTA_THREADS + 32, kMaxSmem, st>>>(an);
+                else
+                    suite_fused_kernel<false, true><<<(unsigned)n_xb, CTA_THREADS, exclusive ? kMaxSmem : an.smem_bytes, st>>>(an);
+                ++n_launch;
+                return cudaGetLastError();
+            };
             SuiteArgs ap = full.a;
             ap.start = p->d_start_c;
-            static const int order = getenv("PQB_COMPACT_ORDER") ? atoi(getenv("PQB_COMPACT_ORDER")) : 0;
-            if (order == 0) {
-                CU(cudaStreamWaitEvent(e->stream, e->ev_pre, 0));
-                static const int delay_us = getenv("PQB_COMPACT_DELAY_US") ? atoi(getenv("PQB_COMPACT_DELAY_US")) : 40;
-                if (delay_us > 0) { delay_kernel<<<1, 32, 0, e->stream>>>((unsigned)delay_us * 1000u); CU(cudaGetLastError()); }
-            }
-            if (order == 2) CU(cudaStreamWaitEvent(e->stream, e->ev_join, 0));      // (tuning: no overlap at all)
-            if ((rc = launch_one(ap, nullptr, nb))) return rc;
-            CU(cudaStreamWaitEvent(e->stream, e->ev_join, 0));
-            CompactArgs Sc{};
-            for (int k = 0; k < PQB_N_OUTPUTS; ++k)
-                if (full.a.out[k] && p->x_out[k] && (stored >> k & 1)) {
-                    if (Sc.n_planes == N_OUT) break;
-                    Sc.src[Sc.n_planes] = p->x_out[k]; Sc.dst[Sc.n_planes] = full.a.out[k]; ++Sc.n_planes;
+            if (direct) {
+                if ((rc = launch_one(ap, nullptr, nb))) return rc;
+                CU(launch_null(e->stream));
+            } else {
+                CU(launch_null(e->aux));
+                CU(cudaEventRecord(e->ev_join, e->aux));
+                static const int order = getenv("PQB_COMPACT_ORDER") ? atoi(getenv("PQB_COMPACT_ORDER")) : 0;
+                if (order == 0) {
+                    CU(cudaStreamWaitEvent(e->stream, e->ev_pre, 0));
+                    static const int delay_us = getenv("PQB_COMPACT_DELAY_US") ? atoi(getenv("PQB_COMPACT_DELAY_US")) : 40;
+                    if (delay_us > 0) { delay_kernel<<<1, 32, 0, e->stream>>>((unsigned)delay_us * 1000u); CU(cudaGetLastError()); }
                 }
-            Sc.symmap = p->d_symmap; Sc.bars_padded = (int)p->bars_padded; Sc.n_slots = (int)(n_xb * SYM);
-            compact_kernel<false><<<dim3((unsigned)(n_xb * SYM), (unsigned)((Sc.n_planes + 7) / 8)), 256, 0, e->stream>>>(Sc);
-            CU(cudaGetLastError());
-            ++n_launch;
+                if (order == 2) CU(cudaStreamWaitEvent(e->stream, e->ev_join, 0));  // (tuning: no overlap at all)
+                if ((rc = launch_one(ap, nullptr, nb))) return rc;
+                CU(cudaStreamWaitEvent(e->stream, e->ev_join, 0));
+                CompactArgs Sc{};
+                for (int k = 0; k < PQB_N_OUTPUTS; ++k)
+                    if (full.a.out[k] && p->x_out[k] && (stored >> k & 1)) {
+                        if (Sc.n_planes == N_OUT) break;
+                        Sc.src[Sc.n_planes] = p->x_out[k]; Sc.dst[Sc.n_planes] = full.a.out[k]; ++Sc.n_planes;
+                    }
+                Sc.symmap = p->d_symmap; Sc.bars_padded = (int)p->bars_padded; Sc.n_slots = (int)(n_xb * SYM);
+                compact_kernel<false><<<dim3((unsigned)(n_xb * SYM), (unsigned)((Sc.n_planes + 7) / 8)), 256, 0, e->stream>>>(Sc);
+                CU(cudaGetLastError());
+                ++n_launch;
+            }
         } else
         if (n_null && n_null < nb) {
             if (!p->d_blist) CU(cudaMalloc(&p->d_blist, (size_t)p->n_blocks * 2 * sizeof(int)));

@@ -17,7 +17,7 @@ prm = N.default_params()
 tot, fused, nl = p.time_device(prm, warmup=2, iters=5)
 base = tot / 5
 print(json.dumps({"config": "no nulls", "symbols": S, "bars": NB, "total_ms": tot / 5, "launches": nl}), flush=True)
-for frac in (0.001, 0.01, 0.05):
+for frac in (0.001, 0.01, 0.05, 0.2):
     n = max(1, int(S * frac))
     ok = np.ones(NB, dtype=bool); ok[2000:2003] = False
     bits = np.packbits(ok, bitorder="little")

@@ -216,3 +216,38 @@ def test_symbol_compaction_few_flagged_symbols_in_a_large_panel():
         m = ref[name][1]
         assert np.array_equal(got[name][0][m].view(np.uint64), ref[name][0][m].view(np.uint64)), name
     panel.close()
+
+
+def test_symbol_compaction_direct_mode_many_flagged_symbols():
+    """More than 1,024 flagged symbols (a third of the panel: delistings): the null-aware kernel runs after the plain one and stores
+    straight into the flagged symbols' own lanes (no write-back pass).  Sampled symbols against the oracle; the whole panel against
+    the chunked host pipeline (per-block dispatch), bit for bit."""
+    import polars_quant_b200 as pq
+    S, N = 3400, 260
+    d = synth.ohlcv(S, N, seed=91)
+    ok = {f: np.ones((S, N), bool) for f in F}
+    rng = np.random.default_rng(12)
+    flagged = sorted(rng.choice(S, size=1100, replace=False).tolist())
+    for i, s in enumerate(flagged):
+        kind = i % 4
+        if kind == 0:
+            for f in F: ok[f][s, N - 20 - (i % 50):] = False      # delisted at different dates
+        elif kind == 1: ok["close"][s, 100 + (i % 40)] = False    # one missing close
+        elif kind == 2: ok["low"][s, 50:53] = False
+        else: ok["volume"][s, :10 + (i % 7)] = False              # volume starts later
+    for s in range(0, S, 11):
+        if s not in flagged:
+            for f in F: ok[f][s, :s % 37] = False                 # leading nulls shared by the fields (plain path)
+    panel = _panel_with_nulls(pq, d, ok)
+    res = panel.compute()
+    sample = flagged[:6] + flagged[-6:] + [0, 1, 11, 22, S - 1] + [s + 1 for s in flagged[100:104] if s + 1 < S]
+    for s in sorted(set(sample)):
+        _check_symbol_against_the_oracle(res, s, d, ok, N)
+    got = {k: (v[0].copy(), v[1].copy()) for k, v in res.items()}
+    panel.run_host(chunk_symbols=32)
+    ref = panel.outputs()
+    for name in pqo.OUTPUT_NAMES:
+        assert np.array_equal(got[name][1], ref[name][1]), name
+        m = ref[name][1]
+        assert np.array_equal(got[name][0][m].view(np.uint64), ref[name][0][m].view(np.uint64)), name
+    panel.close()
