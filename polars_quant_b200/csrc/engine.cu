@@ -100,6 +100,9 @@ struct pqb_engine {
     std::mutex mu;                       // guards the single-column scratch panel
     pqb_panel *scratch = nullptr;
     int64_t scratch_bars = 0;
+    // a few one-symbol scratch panels of the lengths seen lately (a frame usually holds columns of one or two lengths; the single-
+    // column entry points used to re-create the scratch -- 4 + 44 planes -- whenever the length changed)
+    std::vector<std::pair<int64_t, pqb_panel *>> scratch_lru;
     pqb_candles *cscratch = nullptr;     // single-column scratch of the candle engine (candles_host.inc)
     int64_t cscratch_bars = 0;
     // pinned staging planes of destroyed panels, kept for the next panel of the same shape: page-locking is the
@@ -336,6 +339,8 @@ extern "C" void pqb_engine_destroy(pqb_engine *e) {
     if (!e) return;
     cudaSetDevice(e->device);
     if (e->scratch) { pqb_panel_destroy(e->scratch); e->scratch = nullptr; }
+    for (auto &kv : e->scratch_lru) pqb_panel_destroy(kv.second);
+    e->scratch_lru.clear();
     if (e->cscratch) { pqb_candles_destroy(e->cscratch); e->cscratch = nullptr; }
     {
         std::lock_guard<std::mutex> lk(e->pool_mu);
@@ -2006,9 +2011,18 @@ static int run_single(pqb_engine *e, const pqb_col *const *cols, const int *fiel
     if (rc) return rc;
     std::lock_guard<std::mutex> lock(e->mu);
     if (!e->scratch || e->scratch_bars != n) {
-        if (e->scratch) { pqb_panel_destroy(e->scratch); e->scratch = nullptr; }
-        rc = pqb_panel_create(e, 1, n, (1u << PQB_N_FIELDS) - 1, (1ull << PQB_N_OUTPUTS) - 1, 1, &e->scratch);
-        if (rc) return rc;
+        // park the current scratch, look for one of this length among the last few, else create it
+        // (short columns only: a one-symbol panel of 1,000,000 bars holds 0.4 GB of pinned memory)
+        if (e->scratch && e->scratch_bars <= 131072) e->scratch_lru.insert(e->scratch_lru.begin(), {e->scratch_bars, e->scratch});
+        else if (e->scratch) pqb_panel_destroy(e->scratch);
+        e->scratch = nullptr;
+        for (size_t i = 0; i < e->scratch_lru.size(); ++i)
+            if (e->scratch_lru[i].first == n) { e->scratch = e->scratch_lru[i].second; e->scratch_lru.erase(e->scratch_lru.begin() + (long)i); break; }
+        while (e->scratch_lru.size() > 3) { pqb_panel_destroy(e->scratch_lru.back().second); e->scratch_lru.pop_back(); }
+        if (!e->scratch) {
+            rc = pqb_panel_create(e, 1, n, (1u << PQB_N_FIELDS) - 1, (1ull << PQB_N_OUTPUTS) - 1, 1, &e->scratch);
+            if (rc) return rc;
+        }
         e->scratch_bars = n;
     }
     pqb_panel *p = e->scratch;
