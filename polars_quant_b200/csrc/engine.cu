@@ -25,6 +25,7 @@
 #include <mutex>
 #include <string>
 #include <thread>
+#include <memory>
 #include <vector>
 
 using namespace pqb;
@@ -118,6 +119,18 @@ struct pqb_engine {
     // 2,000 x 2,520 (cudaFree synchronises the device); PQB_DEV_POOL_MB, default 4096
     std::multimap<size_t, void *> dev_pool;
     size_t dev_pool_bytes = 0, dev_pool_cap = 4ull << 30;
+};
+
+// CUDA events that are destroyed on every way out of a function (the CU() macro returns early)
+struct Events {
+    std::vector<cudaEvent_t> ev;
+    explicit Events(size_t n) : ev(n, nullptr) {}
+    ~Events() { for (cudaEvent_t x : ev) if (x) cudaEventDestroy(x); }
+    cudaEvent_t &operator[](size_t i) { return ev[i]; }
+    cudaError_t create(unsigned flags = cudaEventDefault) {
+        for (cudaEvent_t &x : ev) { const cudaError_t ce = cudaEventCreateWithFlags(&x, flags); if (ce != cudaSuccess) return ce; }
+        return cudaSuccess;
+    }
 };
 
 // page-locked host memory placed next to the engine's GPU (columns_host.inc: the calling thread runs on the GPU-local
@@ -268,6 +281,8 @@ static int set_dev(const pqb_engine *e) {
     return PQB_OK;
 }
 
+static void engine_free(pqb_engine *e);
+
 extern "C" int pqb_engine_create(int device, pqb_engine **out) {
     if (!out) return fail(PQB_ERR_INVALID, "pqb_engine_create: out is NULL");
     *out = nullptr;
@@ -285,6 +300,7 @@ extern "C" int pqb_engine_create(int device, pqb_engine **out) {
         return fail(PQB_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", device,
                     pr.major, pr.minor);
     pqb_engine *e = new pqb_engine();
+    std::unique_ptr<pqb_engine, void (*)(pqb_engine *)> guard(e, engine_free);       // (freed on every early return below)
     e->device = device;
     e->sm_count = pr.multiProcessorCount;
     if (const char *hp = getenv("PQB_HOST_POOL_MB")) e->host_pool_cap = (size_t)std::max(0, atoi(hp)) << 20;   // 0: no pooling
@@ -316,6 +332,7 @@ extern "C" int pqb_engine_create(int device, pqb_engine **out) {
     CU(cudaFuncSetAttribute(suite_fused_kernel<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     CU(cudaFuncSetAttribute(suite_fused_kernel<false, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
     CU(cudaFuncSetAttribute(suite_fused_kernel<false, false, false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    guard.release();
     *out = e;
     return PQB_OK;
 }
@@ -1622,9 +1639,9 @@ static int run_host_impl(pqb_panel *p, const pqb_suite_params *sp, int64_t chunk
     chunk_symbols = std::max<int64_t>(SYM, chunk_symbols / SYM * SYM);
     const int64_t n_chunks = (p->n_symbols + chunk_symbols - 1) / chunk_symbols;
     const size_t cplane = (size_t)p->chunk_symbols * p->pitch;
-    std::vector<cudaEvent_t> up((size_t)n_chunks), done((size_t)n_chunks);
-    for (auto &x : up) CU(cudaEventCreateWithFlags(&x, cudaEventDisableTiming));
-    for (auto &x : done) CU(cudaEventCreateWithFlags(&x, cudaEventDisableTiming));
+    Events up((size_t)n_chunks), done((size_t)n_chunks);
+    CU(up.create(cudaEventDisableTiming));
+    CU(done.create(cudaEventDisableTiming));
     // null bookkeeping -> device: the whole panel up front, or (pipelined intake) chunk by chunk as the columns arrive
     if (!gate && (rc = prepare_nulls(p, e->h2d))) return rc;
     int total_launches = 0;
@@ -1680,8 +1697,6 @@ static int run_host_impl(pqb_panel *p, const pqb_suite_params *sp, int64_t chunk
     CU(cudaStreamSynchronize(e->d2h));
     CU(cudaStreamSynchronize(e->stream));
     CU(cudaStreamSynchronize(e->h2d));
-    for (auto &x : up) cudaEventDestroy(x);
-    for (auto &x : done) cudaEventDestroy(x);
     p->last_launches = total_launches;
     p->inputs_resident = true;
     return PQB_OK;
@@ -1761,12 +1776,11 @@ extern "C" int pqb_suite_time(pqb_panel *p, const pqb_suite_params *sp, int warm
     for (int i = 0; i < warmup; ++i)
         if ((rc = run_suite(p, sp, nullptr, &nl))) return rc;
     CU(cudaStreamSynchronize(st));
-    std::vector<cudaEvent_t> b((size_t)iters), a((size_t)iters);
-    for (auto &x : b) CU(cudaEventCreate(&x));
-    for (auto &x : a) CU(cudaEventCreate(&x));
-    cudaEvent_t e0, e1;
-    CU(cudaEventCreate(&e0));
-    CU(cudaEventCreate(&e1));
+    Events b((size_t)iters), a((size_t)iters), e01(2);
+    CU(b.create());
+    CU(a.create());
+    CU(e01.create());
+    cudaEvent_t e0 = e01[0], e1 = e01[1];
     CU(cudaEventRecord(e0, st));
     for (int i = 0; i < iters; ++i) {
         CU(cudaEventRecord(b[(size_t)i], st));
@@ -1781,10 +1795,6 @@ extern "C" int pqb_suite_time(pqb_panel *p, const pqb_suite_params *sp, int warm
         CU(cudaEventElapsedTime(&t, b[(size_t)i], a[(size_t)i]));
         fused += t;
     }
-    for (auto &x : b) cudaEventDestroy(x);
-    for (auto &x : a) cudaEventDestroy(x);
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
     if (ms_total) *ms_total = tot;
     if (ms_fused) *ms_fused = fused;
     if (launches_per_step) *launches_per_step = nl;
@@ -1800,9 +1810,9 @@ extern "C" int pqb_suite_time_host(pqb_panel *p, const pqb_suite_params *sp, int
         if ((rc = pqb_suite_run_host(p, sp, chunk_symbols))) return rc;
     // the whole pipeline spans three streams; bracket it with device-wide syncs and events on the
     // first / last stream of the pipeline
-    cudaEvent_t e0, e1;
-    CU(cudaEventCreate(&e0));
-    CU(cudaEventCreate(&e1));
+    Events e01(2);
+    CU(e01.create());
+    cudaEvent_t e0 = e01[0], e1 = e01[1];
     CU(cudaDeviceSynchronize());
     CU(cudaEventRecord(e0, p->e->h2d));
     for (int i = 0; i < iters; ++i)
@@ -1811,8 +1821,6 @@ extern "C" int pqb_suite_time_host(pqb_panel *p, const pqb_suite_params *sp, int
     CU(cudaEventSynchronize(e1));
     float tot = 0.f;
     CU(cudaEventElapsedTime(&tot, e0, e1));
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
     if (ms_total) *ms_total = tot;
     return PQB_OK;
 }
