@@ -160,6 +160,7 @@ def lib() -> C.CDLL:
         L.pqb_flush_l2.argtypes = [C.c_void_p]
         L.pqb_stream_mix.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_int, C.POINTER(C.c_float)]
         L.pqb_probe_pcie.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.POINTER(C.c_double)]
+        L.pqb_panel_clear_validity.argtypes = [C.c_void_p, C.c_int]
         L.pqb_donchian.argtypes = [C.c_void_p, C.POINTER(Col), C.POINTER(Col), C.c_int32, C.POINTER(OutCol), C.POINTER(OutCol)]
         L.pqb_dm.argtypes = [C.c_void_p, C.POINTER(Col), C.POINTER(Col), C.POINTER(Col), C.c_int32] + [C.POINTER(OutCol)] * 6
         L.pqb_selftest_divsqrt.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_uint64)]

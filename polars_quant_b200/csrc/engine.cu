@@ -558,6 +558,17 @@ extern "C" int pqb_panel_set_column(pqb_panel *p, int64_t symbol, int field, con
     return stage_column(p, symbol, field, values, 'g', validity, offset, len);
 }
 
+extern "C" int pqb_panel_clear_validity(pqb_panel *p, int field) {
+    if (!p || field >= PQB_N_FIELDS) return fail(PQB_ERR_INVALID, "pqb_panel_clear_validity: bad argument");
+    for (int f = 0; f < PQB_N_FIELDS; ++f) {
+        if (field >= 0 && f != field) continue;
+        std::fill(p->h_lead[f].begin(), p->h_lead[f].end(), -1);
+        p->h_vin[f].clear();
+        for (auto &fl : p->h_flags) fl &= (uint8_t)~(1u << f);
+    }
+    return PQB_OK;
+}
+
 extern "C" int pqb_panel_set_starts(pqb_panel *p, const int32_t *starts) {
     if (!p || !starts) return fail(PQB_ERR_INVALID, "pqb_panel_set_starts: NULL argument");
     for (int64_t s = 0; s < p->n_symbols; ++s) {

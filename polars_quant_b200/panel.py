@@ -129,6 +129,8 @@ class Panel:
             v = self.host_field(name)
             v[:, :self.n_bars] = a
             v[:, self.n_bars:] = 0.0
+            # (dense values written past the column intake: whatever validity earlier set_column calls recorded is void)
+            N.check(N.lib().pqb_panel_clear_validity(self._h, self.FIELDS[name]))
         if starts is not None:
             s = np.ascontiguousarray(starts, dtype=np.int32)
             N.check(N.lib().pqb_panel_set_starts(self._h, s.ctypes.data_as(C.c_void_p)))

@@ -251,3 +251,33 @@ def test_symbol_compaction_direct_mode_many_flagged_symbols():
         m = ref[name][1]
         assert np.array_equal(got[name][0][m].view(np.uint64), ref[name][0][m].view(np.uint64)), name
     panel.close()
+
+
+def test_a_reused_panel_forgets_the_nulls_of_overwritten_fields():
+    """A panel that held columns with interior nulls and is then refilled with dense matrices (Panel.set_fields writes the
+    pinned planes directly) must not stay in null-aware mode on stale validity: every output equals the plain oracle and the
+    optional groups, which the null-aware kernel refuses, run."""
+    import polars_quant_b200 as pq
+    from polars_quant_b200 import _native as NV
+    S, N = 40, 300
+    d = synth.ohlcv(S, N, seed=5)
+    ok = _null_masks(S, N, seed=2)
+    panel = _panel_with_nulls(pq, d, ok)
+    panel.compute()                                            # null-aware run
+    d2 = synth.ohlcv(S, N, seed=6)
+    panel.set_fields(close=d2["close"], high=d2["high"], low=d2["low"], volume=d2["volume"])
+    res = panel.compute()
+    out, okk, _ = pqo.suite_panel(d2["close"], d2["high"], d2["low"], d2["volume"])
+    fails = T.compare_all(res, out, okk, pqo.OUTPUT_NAMES)
+    assert not fails, "\n".join(fails[:5])
+    panel.close()
+    p2 = pq.Panel(S, N, outputs_mask=(1 << NV.N_SUITE_OUTPUTS) - 1 | 1 << NV.OUTPUT_NAMES.index("mom"))
+    for s in range(S):
+        bits = np.packbits(ok["close"][s].astype(np.uint8), bitorder="little")
+        p2.set_column(s, "close", d["close"][s], validity=bits)
+    p2.set_fields(close=d2["close"], high=d2["high"], low=d2["low"], volume=d2["volume"])
+    res = p2.compute(NV.default_params(indicators=NV.IND_ALL | NV.IND_EXTRA["mom"]))     # refused on a panel with interior nulls
+    mv, mk = pqo.mom(d2["close"][3], 10)
+    nbad, msg = T.compare("mom", res["mom"][0][3], res["mom"][1][3], mv, mk)
+    assert nbad == 0, msg
+    p2.close()
