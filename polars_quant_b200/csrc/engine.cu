@@ -1168,7 +1168,7 @@ static int build_args(const pqb_panel *p, const pqb_suite_params *sp, Built *out
     return layout_rings(A, p);
 }
 
-#ifdef PQB_DEBUG_CLOCKS
+#if defined(PQB_DEBUG_CLOCKS) || defined(PQB_DEBUG_SMID)
 static unsigned long long *g_dbg = nullptr;
 #endif
 
@@ -1308,8 +1308,8 @@ static int launch_suite(pqb_panel *p, const Built &full, int64_t b0, int64_t nb,
         a.block0 = list ? 0 : (int)b0;
         a.blist = list;
         derive_roles(a);
-#ifdef PQB_DEBUG_CLOCKS      // tuning build: per-role busy cycles of the first block (costs ~18% on config 4)
-        if (!g_dbg) CU(cudaMalloc(&g_dbg, N_ROLES * sizeof(unsigned long long)));
+#if defined(PQB_DEBUG_CLOCKS) || defined(PQB_DEBUG_SMID)      // tuning builds: per-role busy cycles of the first block (costs ~18% on config 4) / the SM of every CTA
+        if (!g_dbg) { CU(cudaMalloc(&g_dbg, 4096 * sizeof(unsigned long long))); CU(cudaMemset(g_dbg, 0xff, 4096 * sizeof(unsigned long long))); }
         a.dbg = g_dbg;
 #else
         a.dbg = nullptr;
@@ -1510,6 +1510,22 @@ static int launch_suite(pqb_panel *p, const Built &full, int64_t b0, int64_t nb,
             if ((rc = launch_one(an, null_list, n_null))) return rc;
         }
     }
+#ifdef PQB_DEBUG_SMID
+    if (g_dbg && full.a.gmask) {
+        static unsigned long long h[4096];
+        CU(cudaStreamSynchronize(e->stream));
+        CU(cudaMemcpy(h, g_dbg, sizeof h, cudaMemcpyDeviceToHost));
+        int whole[256] = {0}, part[256] = {0};
+        for (int i = 0; i < 2048; ++i) if (h[i] < 256) ++whole[h[i]];
+        for (int i = 2048; i < 4096; ++i) if (h[i] < 256) ++part[h[i]];
+        int hist[8][8] = {{0}};
+        for (int s = 0; s < e->sm_count; ++s) ++hist[std::min(whole[s], 7)][std::min(part[s], 7)];
+        fprintf(stderr, "[pqb] SMs by (whole-block CTAs, tail CTAs):");
+        for (int w = 0; w < 8; ++w) for (int t = 0; t < 8; ++t) if (hist[w][t]) fprintf(stderr, " (%d,%d)x%d", w, t, hist[w][t]);
+        fprintf(stderr, "\n");
+        CU(cudaMemset(g_dbg, 0xff, sizeof h));
+    }
+#endif
 #ifdef PQB_DEBUG_CLOCKS
     if (g_dbg && full.a.gmask) {
         unsigned long long h[N_ROLES];

@@ -51,21 +51,27 @@ def _null_masks(S, N, seed, frac=0.03):
     return ok
 
 
-def _check_symbol_against_the_oracle(res, s, d, ok, N):
+_DEFAULT_PERIODS = dict(sma_period=30, ema_period=30, tema_period=30, trima_period=30, bbands_period=20, bbands_nbdevup=2.0, bbands_nbdevdn=2.0,
+                        macd_fast=12, macd_slow=26, macd_signal=9, rsi_period=14, atr_period=14, natr_period=14,
+                        kdj_fastk=9, kdj_slowk=3, kdj_slowd=3)
+
+
+def _check_symbol_against_the_oracle(res, s, d, ok, N, P=_DEFAULT_PERIODS):
     c, h, l, v = (d[f] for f in F)
     kc, kh, kl, kv = (ok[f] for f in F)
-    _check("sma", res, s, pqo.sma(c[s], 30, kc[s]))
-    _check("ema", res, s, pqo.ema(c[s], 30, kc[s]))
-    _check("tema", res, s, pqo.tema(c[s], 30, kc[s]))
-    _check("trima", res, s, pqo.trima(c[s], 30, kc[s]))
-    for name, ref in zip(("bb_upper", "bb_middle", "bb_lower"), pqo.bbands(c[s], 20, 2.0, 2.0, kc[s])):
+    _check("sma", res, s, pqo.sma(c[s], P["sma_period"], kc[s]))
+    _check("ema", res, s, pqo.ema(c[s], P["ema_period"], kc[s]))
+    _check("tema", res, s, pqo.tema(c[s], P["tema_period"], kc[s]))
+    _check("trima", res, s, pqo.trima(c[s], P["trima_period"], kc[s]))
+    for name, ref in zip(("bb_upper", "bb_middle", "bb_lower"),
+                         pqo.bbands(c[s], P["bbands_period"], P["bbands_nbdevup"], P["bbands_nbdevdn"], kc[s])):
         _check(name, res, s, ref)
     _check("trange", res, s, pqo.trange(h[s], l[s], c[s], kh[s], kl[s], kc[s]))
-    _check("atr", res, s, pqo.atr(h[s], l[s], c[s], 14, kh[s], kl[s], kc[s]))
-    _check("natr", res, s, pqo.natr(h[s], l[s], c[s], 14, kh[s], kl[s], kc[s]))
+    _check("atr", res, s, pqo.atr(h[s], l[s], c[s], P["atr_period"], kh[s], kl[s], kc[s]))
+    _check("natr", res, s, pqo.natr(h[s], l[s], c[s], P["natr_period"], kh[s], kl[s], kc[s]))
     _check("obv", res, s, pqo.obv(c[s], v[s], kc[s], kv[s]))
     _check("ad", res, s, pqo.ad(h[s], l[s], c[s], v[s], kh[s], kl[s], kc[s], kv[s]))
-    sk, sd = pqo.stoch(h[s], l[s], c[s], 9, 3, 0, 3, 0, kh[s], kl[s], kc[s])
+    sk, sd = pqo.stoch(h[s], l[s], c[s], P["kdj_fastk"], P["kdj_slowk"], 0, P["kdj_slowd"], 0, kh[s], kl[s], kc[s])
     _check("kdj_k", res, s, sk)
     _check("kdj_d", res, s, sd)
     jok = sk[1] & sd[1]
@@ -75,11 +81,11 @@ def _check_symbol_against_the_oracle(res, s, d, ok, N):
     clean = {f: ok[f][s].all() or lead_only[f] for f in F}
     a = int(np.argmax(kc[s]))
     if clean["close"]:
-        for name, ref in zip(("macd", "macd_signal", "macd_hist"), pqo.macd(c[s, a:], 12, 26, 9)):
+        for name, ref in zip(("macd", "macd_signal", "macd_hist"), pqo.macd(c[s, a:], P["macd_fast"], P["macd_slow"], P["macd_signal"])):
             full_v = np.full(N, np.nan); full_k = np.zeros(N, bool)
             full_v[a:], full_k[a:] = ref
             _check(name, res, s, (full_v, full_k))
-        rv, rk = pqo.rsi(c[s, a:], 14)
+        rv, rk = pqo.rsi(c[s, a:], P["rsi_period"])
         full_v = np.full(N, np.nan); full_k = np.zeros(N, bool); full_v[a:], full_k[a:] = rv, rk
         _check("rsi", res, s, (full_v, full_k))
     else:
@@ -281,3 +287,28 @@ def test_a_reused_panel_forgets_the_nulls_of_overwritten_fields():
     nbad, msg = T.compare("mom", res["mom"][0][3], res["mom"][1][3], mv, mk)
     assert nbad == 0, msg
     p2.close()
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_null_mode_random_periods_and_null_patterns(seed):
+    """Random periods (1 included) x random null patterns: the null-aware walk keeps its per-function rules whatever the window
+    lengths are -- windows shorter than a gap, longer than the listed history, period-1 quirks."""
+    import polars_quant_b200 as pq
+    from polars_quant_b200 import _native as Nn
+    rng = np.random.default_rng(4200 + seed)
+    r = lambda lo, hi: int(rng.integers(lo, hi + 1))
+    fast = r(1, 15)
+    P = dict(sma_period=r(1, 60), ema_period=r(1, 60), tema_period=r(1, 25), trima_period=r(1, 60), bbands_period=r(1, 50),
+             bbands_nbdevup=1.5, bbands_nbdevdn=2.5, macd_fast=fast, macd_slow=fast + r(1, 20), macd_signal=r(1, 12), rsi_period=r(1, 30),
+             atr_period=r(1, 30), natr_period=r(1, 30), kdj_fastk=r(1, 40), kdj_slowk=r(1, 8), kdj_slowd=r(1, 8))
+    if seed % 2:
+        P["natr_period"] = P["atr_period"]
+        P["ema_period"] = P["tema_period"]
+    S, N = 40, 500
+    d = synth.ohlcv(S, N, seed=700 + seed)
+    ok = _null_masks(S, N, seed=50 + seed, frac=(0.002, 0.03, 0.15)[seed % 3])
+    panel = _panel_with_nulls(pq, d, ok)
+    res = panel.compute(Nn.default_params(**P))
+    for s in range(S):
+        _check_symbol_against_the_oracle(res, s, d, ok, N, P)
+    panel.close()
