@@ -666,8 +666,8 @@ static int prepare_compaction(pqb_panel *p, cudaStream_t st) {
 // The choice is per BLOCK (launch_suite makes one launch per kind over block lists), derived from what the columns
 // currently hold -- nothing sticky: overwriting a column with a null-free one returns its block to the plain kernel.
 // Ships starts / masks / flags of the range to the device on stream `st`.
-static int prepare_nulls(pqb_panel *p, cudaStream_t st, int64_t s0 = 0, int64_t ns = -1) {
-    if (ns < 0) ns = p->n_symbols - s0;
+// host half: which blocks need the null-aware kernel, the per-symbol starts; returns whether any block of the range does
+static bool prepare_nulls_host(pqb_panel *p, int64_t s0, int64_t ns) {
     const int64_t b0 = s0 / SYM, b1 = (s0 + ns + SYM - 1) / SYM;
     bool any_null = false;
     for (int64_t b = b0; b < b1; ++b) {
@@ -696,7 +696,13 @@ static int prepare_nulls(pqb_panel *p, cudaStream_t st, int64_t s0 = 0, int64_t 
     }
     p->nulls_mode = p->n_null_blocks > 0;
     p->compact = false;
-    CU(cudaMemcpyAsync(p->d_start + s0, p->h_start.data() + s0, (size_t)ns * sizeof(int), cudaMemcpyHostToDevice, st));
+    return any_null;
+}
+// device half (copy_start = false: the caller's pack launch writes the starts itself, run_single's mapped path)
+static int prepare_nulls_device(pqb_panel *p, cudaStream_t st, int64_t s0, int64_t ns, bool any_null, bool copy_start) {
+    const int64_t b0 = s0 / SYM, b1 = (s0 + ns + SYM - 1) / SYM;
+    if (copy_start)
+        CU(cudaMemcpyAsync(p->d_start + s0, p->h_start.data() + s0, (size_t)ns * sizeof(int), cudaMemcpyHostToDevice, st));
     if (!any_null) return PQB_OK;
     const size_t bplane = (size_t)p->n_symbols * p->words_per_row * sizeof(uint32_t);
     const size_t mwords = (size_t)p->n_blocks * p->bars_padded;
@@ -724,12 +730,17 @@ static int prepare_nulls(pqb_panel *p, cudaStream_t st, int64_t s0 = 0, int64_t 
     if (s0 == 0 && ns == p->n_symbols) return prepare_compaction(p, st);
     return PQB_OK;
 }
+static int prepare_nulls(pqb_panel *p, cudaStream_t st, int64_t s0 = 0, int64_t ns = -1) {
+    if (ns < 0) ns = p->n_symbols - s0;
+    return prepare_nulls_device(p, st, s0, ns, prepare_nulls_host(p, s0, ns), true);
+}
 
 // ---- layout conversion launches (chunk = symbols [s0, s0+ns), s0 a multiple of 32) ----
 static int launch_conv(pqb_panel *p, bool pack, const double *const *rowmajor, double *const *tiled, int n_planes,
-                       int64_t s0, int64_t ns, cudaStream_t st) {
+                       int64_t s0, int64_t ns, cudaStream_t st, const ConvArgs *extra = nullptr) {
     if (n_planes == 0 || ns == 0) return PQB_OK;
     ConvArgs V{};
+    if (extra) V = *extra;                                    // (riders of run_single's mapped path: starts / validity words)
     V.n_planes = n_planes;
     for (int i = 0; i < n_planes; ++i) {
         if (pack) { V.src[i] = rowmajor[i]; V.dst[i] = tiled[i]; }
@@ -2072,7 +2083,25 @@ static int run_single(pqb_engine *e, const pqb_col *const *cols, const int *fiel
     // only what this call touches crosses PCIe: the given fields up, the requested outputs down (the scratch panel has
     // every plane allocated; one EMA on a 1 M-bar column used to move 43 result planes)
     cudaStream_t st = e->stream;
-    {
+    // short columns: no copy engine at all -- the pack kernel reads the pinned staging through its mapping and carries the
+    // start, the unpack kernel writes values and validity words straight into the pinned result planes (a 2 KB column paid
+    // ~12 us per cudaMemcpyAsync, 4 - 8 of them per call: EMA 104 us, MACD / BBANDS 165 us).  PQB_SINGLE_MAPPED = largest such
+    // column in bars (0: always the copy engine)
+    static const int64_t mapped_max = getenv("PQB_SINGLE_MAPPED") ? atoll(getenv("PQB_SINGLE_MAPPED")) : 32768;
+    const bool mapped = n <= mapped_max && n_out <= CONV_MAX_BITS;
+    if (mapped) {
+        const double *rm[PQB_N_FIELDS];
+        double *tl[PQB_N_FIELDS];
+        int nf = 0;
+        for (int f = 0; f < PQB_N_FIELDS; ++f)
+            if (fmask >> f & 1) { rm[nf] = p->h_in[f]; tl[nf] = p->d_in[f]; ++nf; }
+        const bool any_null = prepare_nulls_host(p, 0, 1);
+        ConvArgs X{};
+        X.start_dst = p->d_start; X.start_val = p->h_start[0];
+        if ((rc = launch_conv(p, true, rm, tl, nf, 0, 1, st, &X))) return rc;
+        p->inputs_resident = true;
+        if ((rc = prepare_nulls_device(p, st, 0, 1, any_null, false))) return rc;
+    } else {
         const double *rm[PQB_N_FIELDS];
         double *tl[PQB_N_FIELDS];
         int nf = 0;
@@ -2088,7 +2117,17 @@ static int run_single(pqb_engine *e, const pqb_col *const *cols, const int *fiel
         if ((rc = prepare_nulls(p, st))) return rc;
     }
     if ((rc = pqb_suite_run(p, sp))) return rc;
-    {
+    if (mapped) {
+        const double *rm[PQB_N_OUTPUTS];
+        double *tl[PQB_N_OUTPUTS];
+        ConvArgs X{};
+        for (int i = 0; i < n_out; ++i) {
+            rm[i] = p->h_out[outs[i]]; tl[i] = p->d_out[outs[i]];
+            X.bits_src[i] = p->d_bits[outs[i]]; X.bits_dst[i] = p->h_bits[outs[i]];
+        }
+        X.n_bits = n_out; X.bits_words = (int)p->words_per_row;
+        if ((rc = launch_conv(p, false, rm, tl, n_out, 0, 1, st, &X))) return rc;
+    } else {
         const double *rm[PQB_N_OUTPUTS];
         double *tl[PQB_N_OUTPUTS];
         const size_t cplane = (size_t)p->chunk_symbols * p->pitch;
