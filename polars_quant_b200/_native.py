@@ -27,6 +27,7 @@ IND_EXTRA = {"midpoint": 1 << 15, "adosc": 1 << 16, "mom": 1 << 17, "roc": 1 << 
              "cci": 1 << 21, "dm": 1 << 22, "trix": 1 << 23, "ultosc": 1 << 24, "aroon": 1 << 25,
              "donchian": 1 << 26}
 IND_ALL = (1 << 15) - 1
+IND_FASTK = 1 << 27          # with IND["kdj"]: also store the raw %K line (output "fastk"); opt-in, the general kernel only
 
 ERR_NAMES = {-1: "PQB_ERR_NO_DEVICE", -2: "PQB_ERR_CUDA", -3: "PQB_ERR_INVALID", -4: "PQB_ERR_UNSUPPORTED",
              -5: "PQB_ERR_NULLS", -6: "PQB_ERR_ALLOC"}

@@ -921,6 +921,8 @@ retry_layout:
     A.off_adx = take((A.gmask & G_DM) ? A.dm_p - 1 : 0);
     A.off_ult = take((A.gmask & G_ULTOSC) ? 2 * std::max(std::max(A.ult_p1, A.ult_p2), A.ult_p3) : 2);
     A.off_arh = take((A.gmask & G_AROON) ? A.aroon_p + 1 : 0); A.off_arl = take((A.gmask & G_AROON) ? A.aroon_p + 1 : 0);
+    A.off_ari = take((A.gmask & G_AROON) ? (A.aroon_p + 2) / 2 : 0);      // packed offsets of the suffix extremes: 4 bytes per lane and slot
+    A.off_art = take((A.gmask & G_AROON) ? (A.aroon_p + SYM) / SYM : 0);    // the p + 1 quotients (position / p) * 100
     A.off_dh = take((A.gmask & G_DONCHIAN) ? A.don_p + 1 : 0); A.off_dl = take((A.gmask & G_DONCHIAN) ? A.don_p + 1 : 0);
     const long long smem = (long long)kFixedSmem + off * 8;
     if (smem > kMaxSmem && A.mid_own && mid_shares) { A.mid_own = 0; goto retry_layout; }   // long windows: share after all
@@ -1078,7 +1080,7 @@ static int build_args(const pqb_panel *p, const pqb_suite_params *sp, Built *out
             A.gmask |= G_KDJ; A.kdj_k = k; A.kdj_sk = sk; A.kdj_sd = sd; A.inv_sk = 1.0 / (double)sk; A.inv_sd = 1.0 / (double)sd;
             bind(PQB_OUT_KDJ_K, (long long)k + sk - 2); bind(PQB_OUT_KDJ_D, (long long)k + sk + sd - 3);
             bind(PQB_OUT_KDJ_J, (long long)k + sk + sd - 3);
-            if (want(PQB_OUT_FASTK)) { A.out[PQB_OUT_FASTK] = p->d_out[PQB_OUT_FASTK]; out->lead[PQB_OUT_FASTK] = NEVER; }   // validity from the kernel
+            if ((sp->indicators & PQB_IND_FASTK) && want(PQB_OUT_FASTK)) { A.out[PQB_OUT_FASTK] = p->d_out[PQB_OUT_FASTK]; out->lead[PQB_OUT_FASTK] = NEVER; }   // validity from the kernel
             upto((long long)k + sk + sd - 2);
         }
     }
@@ -1632,7 +1634,7 @@ static int launch_suite(pqb_panel *p, const Built &full, int64_t b0, int64_t nb,
 
 // the optional groups report validity per bar: allocate their validity-word planes on first use
 static int ensure_extra_masks(pqb_panel *p, const pqb_suite_params *sp) {
-    if (!(sp->indicators & PQB_IND_EXTRAS) && !p->d_out[PQB_OUT_FASTK]) return PQB_OK;
+    if (!(sp->indicators & (PQB_IND_EXTRAS | PQB_IND_FASTK))) return PQB_OK;
     const size_t mwords = (size_t)p->n_blocks * p->bars_padded;
     for (int k = PQB_N_SUITE_OUTPUTS; k < PQB_N_OUTPUTS; ++k)
         if (p->d_out[k] && !p->d_ovm[k]) CU(cudaMalloc(&p->d_ovm[k], mwords * sizeof(uint32_t)));

@@ -42,7 +42,7 @@ def test_no_cpu_fallback_without_a_device(lib):
     import torch
     if torch.cuda.is_available():
         pytest.skip("a GPU is present")
-    assert lib.pqb_abi_version() == 6
+    assert lib.pqb_abi_version() == 7
     assert lib.pqb_device_count() == 0
     h = C.c_void_p()
     rc = lib.pqb_engine_create(0, C.byref(h))

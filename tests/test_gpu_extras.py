@@ -222,6 +222,36 @@ def test_trix_ultosc_aroon_through_the_plugin_names_and_edge_cases():
         talib.AROON(ah, al, 0)
 
 
+@pytest.mark.parametrize("period", [1, 2, 3, 14, 31, 32, 33, 100])
+def test_aroon_positions_with_ties_nan_and_infinities(period):
+    """aroon momentum.rs:63-110 through the block-decomposed window (suffix summaries of the previous p+1 bars + the running
+    prefix): `>=` / `<=` scans from f64::MIN / f64::MAX -- the LAST of equal extremes wins, a NaN is never taken, neither is
+    -inf as a high or +inf as a low (nothing taken at all leaves position 0), +-f64::MAX are ordinary values."""
+    import pyarrow as pa
+    from polars_quant_b200 import talib
+    rng = np.random.default_rng(period)
+    n = 1500
+    h = np.round(rng.normal(100.0, 2.0, n), 0)                # coarse grid: many exact ties inside a window
+    l = h - np.round(rng.uniform(0.0, 3.0, n), 0)
+    fmax = np.finfo(np.float64).max
+    for k, (hv, lv) in enumerate([(np.nan, np.nan), (-np.inf, np.inf), (np.inf, -np.inf), (-fmax, fmax), (fmax, -fmax)]):
+        at = rng.choice(n, 25, replace=False)
+        h[at] = hv
+        l[at[::2]] = lv
+    h[700:700 + 3 * period + 5] = np.nan                      # whole windows without a qualifying high
+    l[900:900 + 3 * period + 5] = np.inf
+    h[1100:1100 + 2 * period + 3] = -np.inf
+    up, dn = talib.AROON(pa.array(h), pa.array(l), period)
+    ru, rd = pqo.aroon(h, l, period)
+    for name, got, r in (("aroon_up", up, ru), ("aroon_down", dn, rd)):
+        ok = ~np.asarray(got.is_null())
+        v = np.where(ok, np.asarray(got.to_numpy(zero_copy_only=False), dtype=np.float64), np.nan)
+        nbad, msg = T.compare("%s(%d)" % (name, period), v, ok, r[0], r[1])
+        assert nbad == 0, msg
+    assert ru[1][period:].all() and not ru[1][:period].any()
+    assert ru[0][700 + period + 2] == 0.0                     # nothing qualifies in the window: position 0
+
+
 def test_crossover_signals_are_exact_functions_of_the_suite_outputs():
     """golden / death crosses of MACD and KDJ and the RSI zone exits as int8, computed on the device from
     the suite's own outputs -- compared with the same rules evaluated in numpy on the oracle's outputs (the rules are
@@ -292,6 +322,30 @@ def test_partial_suite_next_to_optional_groups_runs_as_two_launches():
         for name in DM_OUT + ("aroon_up", "aroon_down", "mom"):
             nbad, msg = T.compare(name, res[name][0][s], res[name][1][s], *refs[name])
             assert nbad == 0, f"symbol {s}: {msg}"
+    panel.close()
+
+
+def test_fastk_plane_is_written_only_on_request_and_does_not_cost_the_suite_its_kernel():
+    """PQB_OUT_FASTK (STOCHF's raw %K, momentum.py:188-195) is stored by the general kernel only.  A panel that merely has the
+    plane (every output allocated) must keep the compile-time-specialised full-suite launch: the line is opt-in
+    (PQB_IND_FASTK, ABI 7).  With the bit the line equals the oracle's fastk; the suite's own outputs are the same both ways."""
+    import polars_quant_b200 as pq
+    from polars_quant_b200 import _native as N
+    d = synth.ohlcv(70, 700, seed=5)
+    S, NB = d["close"].shape
+    panel = pq.Panel(S, NB, outputs_mask=(1 << N.N_OUTPUTS) - 1)
+    panel.set_fields(d["close"], d["high"], d["low"], d["volume"])
+    res = panel.compute(N.default_params(indicators=N.IND_ALL))
+    assert not res["fastk"][1].any()                          # not requested: all null
+    plain = {k: (v[0].copy(), v[1].copy()) for k, v in res.items() if k.startswith("kdj_") or k in ("sma", "willr")}
+    res = panel.compute(N.default_params(indicators=N.IND_ALL | N.IND_FASTK))
+    for s in range(S):
+        fk = pqo.stochf(d["high"][s], d["low"][s], d["close"][s], 9, 3, 0)[0]
+        nbad, msg = T.compare("fastk", res["fastk"][0][s], res["fastk"][1][s], fk[0], fk[1])
+        assert nbad == 0, f"symbol {s}: {msg}"
+    for k, (v, ok) in plain.items():
+        nbad, msg = T.compare(k, res[k][0], res[k][1], v, ok)
+        assert nbad == 0, msg
     panel.close()
 
 
