@@ -1391,12 +1391,46 @@ static int launch_suite(pqb_panel *p, const Built &full, int64_t b0, int64_t nb,
             suite_fused_kernel<true, false, false, true><<<grid, CTA_THREADS_X, a.smem_bytes, e->stream>>>(a);
         else if (fulls && force_base()) {                   // tuning: the partial-suite kernel (seven warps, pipelined roles) on the full suite
             deal_base_slots(a);
+            a.stage_stride = STAGE_BYTES;
             suite_fused_kernel<false, false, true><<<grid, CTA_THREADS, a.smem_bytes, e->stream>>>(a);
         }
         else if (fulls) suite_fused_kernel<true, false><<<grid, CTA_THREADS, fulls_smem(a.smem_bytes), e->stream>>>(a);
         else if (!(a.gmask & ~(unsigned)G_ALL) && !fastk) {
             deal_base_slots(a);
-            suite_fused_kernel<false, false, true><<<grid, CTA_THREADS, a.smem_bytes, e->stream>>>(a);
+            // A partial suite has few role warps per block, so an eight-warp CTA (three per SM by registers) leaves a large panel
+            // latency-bound AND in many waves of equal serial walks (50,000 x 5,040, EMA alone: 4 waves of 0.31 ms).  Two measures
+            // (profiles/r05_partial_suite_cta_shapes.txt): the TMA stages hold only the fields this launch reads (close alone: 2 KB
+            // per stage instead of 8), and the CTA is launched with W warps, n_slots + 1 <= W <= 8 -- the W with the fewest waves,
+            // the widest such (fewer co-resident walks are faster walks).  EMA 1.24 -> 0.81 ms, RSI 2.36 -> 1.85, BBANDS 2.10 -> 1.68.
+            // tuning: PQB_BASE_SLIM=0 full-size stages, PQB_BASE_WARPS=W fixes the width (8 = as before), PQB_BASE_SMEM = dynamic
+            // shared memory to ask for at least, PQB_PRINT_OCC=1 prints the choice
+            static const bool slim = !getenv("PQB_BASE_SLIM") || atoi(getenv("PQB_BASE_SLIM")) != 0;
+            static const int warps = getenv("PQB_BASE_WARPS") ? atoi(getenv("PQB_BASE_WARPS")) : 0;
+            static const int min_smem = getenv("PQB_BASE_SMEM") ? atoi(getenv("PQB_BASE_SMEM")) : 0;
+            int top = 0;
+            for (int f = 0; f < N_IN; ++f) if (a.fields >> f & 1) top = f + 1;
+            a.stage_stride = slim ? top * SB * SYM * 8 : STAGE_BYTES;
+            const int smem = std::max(a.smem_bytes - NS * (STAGE_BYTES - a.stage_stride), min_smem);
+            int threads = CTA_THREADS, occ = 0;
+            if (warps > 0) threads = 32 * std::min(N_ROLES + 1, std::max(warps, a.n_roles + 1));
+            else if (a.split_from < 0 && nb > 3ll * e->sm_count) {          // (up to three blocks per SM the eight-warp CTA is one wave already)
+                int64_t best = INT64_MAX;
+                for (int W = N_ROLES + 1; W > a.n_roles; --W) {
+                    // (warp w runs on SM sub-partition w % 4: the producer -- the last warp, polling its mbarriers -- must not share
+                    // one with a role warp while a sub-partition without one exists: KDJ + ATR with W = 6 took 3.76 ms, W = 8 2.96)
+                    if (a.n_roles < 4 && (W - 1) % 4 < a.n_roles) continue;
+                    if (W > 4 && W <= N_ROLES) continue;      // (5 - 7 warps measured erratic: WILLR + MIDPRICE 4.17 ms with 4 or 8 warps, 4.72 with 6)
+                    int k = 0;
+                    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&k, suite_fused_kernel<false, false, true>, 32 * W, (size_t)smem) != cudaSuccess || k <= 0) continue;
+                    const int64_t waves = (nb + (int64_t)k * e->sm_count - 1) / ((int64_t)k * e->sm_count);
+                    if (waves < best) { best = waves; threads = 32 * W; occ = k; }
+                }
+            }
+            if (getenv("PQB_PRINT_OCC")) {
+                if (!occ) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, suite_fused_kernel<false, false, true>, threads, (size_t)smem);
+                fprintf(stderr, "[pqb] partial suite: %d slots, %d threads, %d B smem -> %d CTAs per SM, grid %u\n", a.n_roles, threads, smem, occ, grid);
+            }
+            suite_fused_kernel<false, false, true><<<grid, threads, smem, e->stream>>>(a);
         }
         else if (wide) suite_fused_kernel<false, false, false, true><<<grid, CTA_THREADS_W, a.smem_bytes, e->stream>>>(a);
         else suite_fused_kernel<false, false><<<grid, CTA_THREADS, a.smem_bytes, e->stream>>>(a);

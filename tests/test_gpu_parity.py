@@ -210,6 +210,36 @@ def test_partial_suites_and_single_indicator_masks(pq):
         panel.close()
 
 
+def test_partial_suites_on_a_many_wave_panel_narrow_ctas(pq):
+    """Beyond three blocks per SM a partial suite is launched with fewer than eight warps per CTA (its slots + the producer at
+    least) and TMA stages that hold only the fields it reads, so that more blocks are resident (engine.cu launch_suite): one,
+    two, three and four slots, close-only / high-low-close / every field, 16,640 symbols = 520 blocks, every symbol against
+    the oracle."""
+    from polars_quant_b200 import _native as N
+    S, NB = 16_640, 160
+    d = synth.ohlcv(S, NB, seed=77)
+    starts = np.zeros(S, np.int32)
+    starts[::97] = 40                                         # a few late listings
+    out, ok = None, None
+    groups_of = {"ema": ["ema"], "rsi": ["rsi"], "bbands": ["bb_upper", "bb_middle", "bb_lower"], "kdj": ["kdj_k", "kdj_d", "kdj_j"],
+                 "atr": ["atr"], "obv": ["obv"], "ad": ["ad"], "sma": ["sma"], "macd": ["macd", "macd_signal", "macd_hist"],
+                 "willr": ["willr"], "midprice": ["midprice"]}
+    for groups in (["ema"], ["rsi"], ["bbands"], ["kdj", "atr"], ["obv", "ad"], ["sma", "ema", "rsi", "macd", "bbands"], ["willr", "midprice"]):
+        if out is None:
+            out, ok = pqo.suite_panel(d["close"], d["high"], d["low"], d["volume"], None)[:2]
+            for s in np.nonzero(starts)[0]:
+                o, k, _ = pqo.suite_panel(*(d[f][s:s + 1, 40:] for f in ("close", "high", "low", "volume")), None)
+                out[:, s, :40], ok[:, s, :40] = np.nan, False
+                out[:, s, 40:], ok[:, s, 40:] = o[:, 0], k[:, 0]
+        names = [o for g in groups for o in groups_of[g]]
+        panel = pq.Panel(S, NB, outputs_mask=sum(1 << pqo.OUTPUT_NAMES.index(o) for o in names))
+        panel.set_fields(d["close"], d["high"], d["low"], d["volume"], starts=starts)
+        res = panel.compute(N.default_params(indicators=sum(N.IND[g] for g in groups)))
+        assert sorted(res) == sorted(names)
+        _assert_parity(res, out, ok)
+        panel.close()
+
+
 def test_period_zero_gives_all_null_columns(pq):
     """timeperiod == 0 -> the reference's guards return an all-null column (overlap.rs:663,874)."""
     from polars_quant_b200 import _native as N
