@@ -1321,6 +1321,37 @@ static int launch_suite(pqb_panel *p, const Built &full, int64_t b0, int64_t nb,
         a.block0 = list ? 0 : (int)b0;
         a.blist = list;
         derive_roles(a);
+        // CTA shape of a launch with few role warps per block (partial suites, optional groups): field-sized stages and the CTA
+        // width with the fewest waves -- see the comment at the partial-suite launch below
+        auto shape_few_warps = [&](const void *kernel, SuiteArgs &x, int n_slots, int &threads, int &smem) {
+            static const bool slim = !getenv("PQB_BASE_SLIM") || atoi(getenv("PQB_BASE_SLIM")) != 0;
+            static const int warps = getenv("PQB_BASE_WARPS") ? atoi(getenv("PQB_BASE_WARPS")) : 0;
+            static const int min_smem = getenv("PQB_BASE_SMEM") ? atoi(getenv("PQB_BASE_SMEM")) : 0;
+            int top = 0;
+            for (int f = 0; f < N_IN; ++f) if (x.fields >> f & 1) top = f + 1;
+            x.stage_stride = slim ? top * SB * SYM * 8 : STAGE_BYTES;
+            smem = std::max(x.smem_bytes - NS * (STAGE_BYTES - x.stage_stride), min_smem);
+            threads = CTA_THREADS;
+            int occ = 0;
+            if (warps > 0) threads = 32 * std::min(N_ROLES + 1, std::max(warps, n_slots + 1));
+            else if (x.split_from < 0 && nb > 3ll * e->sm_count) {          // (up to three blocks per SM the eight-warp CTA is one wave already)
+                int64_t best = INT64_MAX;
+                for (int W = N_ROLES + 1; W > n_slots; --W) {
+                    // (warp w runs on SM sub-partition w % 4: the producer -- the last warp, polling its mbarriers -- must not share
+                    // one with a role warp while a sub-partition without one exists: KDJ + ATR with W = 6 took 3.76 ms, W = 8 2.96)
+                    if (n_slots < 4 && (W - 1) % 4 < n_slots) continue;
+                    if (W > 4 && W <= N_ROLES) continue;      // (5 - 7 warps measured erratic: WILLR + MIDPRICE 4.17 ms with 4 or 8 warps, 4.72 with 6)
+                    int k = 0;
+                    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&k, kernel, 32 * W, (size_t)smem) != cudaSuccess || k <= 0) continue;
+                    const int64_t waves = (nb + (int64_t)k * e->sm_count - 1) / ((int64_t)k * e->sm_count);
+                    if (waves < best) { best = waves; threads = 32 * W; occ = k; }
+                }
+            }
+            if (getenv("PQB_PRINT_OCC")) {
+                if (!occ) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, threads, (size_t)smem);
+                fprintf(stderr, "[pqb] few-warp launch: %d slots, %d threads, %d B smem -> %d CTAs per SM, %lld blocks\n", n_slots, threads, smem, occ, (long long)nb);
+            }
+        };
 #if defined(PQB_DEBUG_CLOCKS) || defined(PQB_DEBUG_SMID)      // tuning builds: per-role busy cycles of the first block (costs ~18% on config 4) / the SM of every CTA
         if (!g_dbg) { CU(cudaMalloc(&g_dbg, 4096 * sizeof(unsigned long long))); CU(cudaMemset(g_dbg, 0xff, 4096 * sizeof(unsigned long long))); }
         a.dbg = g_dbg;
@@ -1404,35 +1435,16 @@ static int launch_suite(pqb_panel *p, const Built &full, int64_t b0, int64_t nb,
             // the widest such (fewer co-resident walks are faster walks).  EMA 1.24 -> 0.81 ms, RSI 2.36 -> 1.85, BBANDS 2.10 -> 1.68.
             // tuning: PQB_BASE_SLIM=0 full-size stages, PQB_BASE_WARPS=W fixes the width (8 = as before), PQB_BASE_SMEM = dynamic
             // shared memory to ask for at least, PQB_PRINT_OCC=1 prints the choice
-            static const bool slim = !getenv("PQB_BASE_SLIM") || atoi(getenv("PQB_BASE_SLIM")) != 0;
-            static const int warps = getenv("PQB_BASE_WARPS") ? atoi(getenv("PQB_BASE_WARPS")) : 0;
-            static const int min_smem = getenv("PQB_BASE_SMEM") ? atoi(getenv("PQB_BASE_SMEM")) : 0;
-            int top = 0;
-            for (int f = 0; f < N_IN; ++f) if (a.fields >> f & 1) top = f + 1;
-            a.stage_stride = slim ? top * SB * SYM * 8 : STAGE_BYTES;
-            const int smem = std::max(a.smem_bytes - NS * (STAGE_BYTES - a.stage_stride), min_smem);
-            int threads = CTA_THREADS, occ = 0;
-            if (warps > 0) threads = 32 * std::min(N_ROLES + 1, std::max(warps, a.n_roles + 1));
-            else if (a.split_from < 0 && nb > 3ll * e->sm_count) {          // (up to three blocks per SM the eight-warp CTA is one wave already)
-                int64_t best = INT64_MAX;
-                for (int W = N_ROLES + 1; W > a.n_roles; --W) {
-                    // (warp w runs on SM sub-partition w % 4: the producer -- the last warp, polling its mbarriers -- must not share
-                    // one with a role warp while a sub-partition without one exists: KDJ + ATR with W = 6 took 3.76 ms, W = 8 2.96)
-                    if (a.n_roles < 4 && (W - 1) % 4 < a.n_roles) continue;
-                    if (W > 4 && W <= N_ROLES) continue;      // (5 - 7 warps measured erratic: WILLR + MIDPRICE 4.17 ms with 4 or 8 warps, 4.72 with 6)
-                    int k = 0;
-                    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&k, suite_fused_kernel<false, false, true>, 32 * W, (size_t)smem) != cudaSuccess || k <= 0) continue;
-                    const int64_t waves = (nb + (int64_t)k * e->sm_count - 1) / ((int64_t)k * e->sm_count);
-                    if (waves < best) { best = waves; threads = 32 * W; occ = k; }
-                }
-            }
-            if (getenv("PQB_PRINT_OCC")) {
-                if (!occ) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, suite_fused_kernel<false, false, true>, threads, (size_t)smem);
-                fprintf(stderr, "[pqb] partial suite: %d slots, %d threads, %d B smem -> %d CTAs per SM, grid %u\n", a.n_roles, threads, smem, occ, grid);
-            }
+            int threads, smem;
+            shape_few_warps((const void *)suite_fused_kernel<false, false, true>, a, a.n_roles, threads, smem);
             suite_fused_kernel<false, false, true><<<grid, threads, smem, e->stream>>>(a);
         }
-        else if (wide) suite_fused_kernel<false, false, false, true><<<grid, CTA_THREADS_W, a.smem_bytes, e->stream>>>(a);
+        else if (wide) {
+            int n_slots = 0, threads, smem;
+            for (int s = 0; s < N_SLOTS_W; ++s) n_slots += (a.gmask & slot_mask_w(s)) ? 1 : 0;
+            shape_few_warps((const void *)suite_fused_kernel<false, false, false, true>, a, n_slots, threads, smem);
+            suite_fused_kernel<false, false, false, true><<<grid, threads, smem, e->stream>>>(a);
+        }
         else suite_fused_kernel<false, false><<<grid, CTA_THREADS, a.smem_bytes, e->stream>>>(a);
         CU(cudaGetLastError());
         ++n_launch;
