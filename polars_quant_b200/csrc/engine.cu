@@ -1347,7 +1347,8 @@ static int launch_suite(pqb_panel *p, const Built &full, int64_t b0, int64_t nb,
                     if (waves < best) { best = waves; threads = 32 * W; occ = k; }
                 }
             }
-            if (getenv("PQB_PRINT_OCC")) {
+            static const bool print_occ = getenv("PQB_PRINT_OCC") != nullptr;
+            if (print_occ) {
                 if (!occ) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, threads, (size_t)smem);
                 fprintf(stderr, "[pqb] few-warp launch: %d slots, %d threads, %d B smem -> %d CTAs per SM, %lld blocks\n", n_slots, threads, smem, occ, (long long)nb);
             }
