@@ -329,6 +329,8 @@ extern "C" int pqb_engine_create(int device, pqb_engine **out) {
     CU(cudaFuncSetAttribute(suite_fused_kernel<false, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
     CU(cudaFuncSetAttribute(suite_fused_kernel<false, true, false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     CU(cudaFuncSetAttribute(suite_fused_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+    CU(cudaFuncSetAttribute(suite_fused_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+    CU(cudaFuncSetAttribute(suite_fused_kernel<true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     CU(cudaFuncSetAttribute(suite_fused_kernel<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     CU(cudaFuncSetAttribute(suite_fused_kernel<false, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
     CU(cudaFuncSetAttribute(suite_fused_kernel<false, false, false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
@@ -1266,7 +1268,20 @@ static void deal_base_slots(SuiteArgs &A) {
 
 // the null-aware variant of a launch's arguments: per-bar validity words in, per-bar validity words out, starts folded
 // into the masks
+// fully valid stages of a null-aware launch run the plain steady step (suite_kernel.cuh run_role): only for launches of the 21 suite
+// outputs -- the optional outputs report validity per bar through emitv, with null rules of their own (PQB_NULLS_FAST=0: never)
+static int nulls_fast_ok(const SuiteArgs &a) {
+    static const bool on = !getenv("PQB_NULLS_FAST") || atoi(getenv("PQB_NULLS_FAST")) != 0;
+    if (!on || (a.gmask & ~(unsigned)G_ALL) || a.don_fold) return 0;
+    for (int k = PQB_N_SUITE_OUTPUTS; k < PQB_N_OUTPUTS; ++k) if (a.out[k]) return 0;
+    return 1;
+}
+static bool nulls_fulls() {              // PQB_NULLS_FULLS=0: the general null-aware kernel also for the full suite
+    static const bool on = !getenv("PQB_NULLS_FULLS") || atoi(getenv("PQB_NULLS_FULLS")) != 0;
+    return on;
+}
 static SuiteArgs null_variant(const pqb_panel *p, SuiteArgs a) {
+    a.nulls_fast = nulls_fast_ok(a);
     a.start = nullptr;
     a.vmask = p->d_vmask;
     a.symflags = p->d_flags;
@@ -1395,7 +1410,8 @@ static int launch_suite(pqb_panel *p, const Built &full, int64_t b0, int64_t nb,
             a.split_parts = std::min(nr, split_all);
             grid = (unsigned)(nb * a.split_parts);
         }
-        if (a.vmask) suite_fused_kernel<false, true><<<grid, CTA_THREADS, a.smem_bytes, e->stream>>>(a);
+        if (a.vmask && fulls && a.nulls_fast && nulls_fulls()) suite_fused_kernel<true, true><<<grid, CTA_THREADS, a.smem_bytes, e->stream>>>(a);
+        else if (a.vmask) suite_fused_kernel<false, true><<<grid, CTA_THREADS, a.smem_bytes, e->stream>>>(a);
         // small panels (about one CTA per SM) are bound by the length of each role's dependent FP64 chain per bar, not by
         // issue slots or HBM: they run the variant whose division-heavy roles (BBANDS, RSI, STOCH) are software-pipelined
         // over bars (suite_kernel.cuh "software-pipelined steady bar"); large panels are throughput-bound and run the
@@ -1490,6 +1506,7 @@ static int launch_suite(pqb_panel *p, const Built &full, int64_t b0, int64_t nb,
             static const int direct_from = getenv("PQB_COMPACT_DIRECT_FROM") ? atoi(getenv("PQB_COMPACT_DIRECT_FROM")) : 1024;
             const bool direct = p->n_x > direct_from;
             SuiteArgs an = full.a;
+            an.nulls_fast = nulls_fast_ok(full.a);
             an.start = nullptr;
             an.vmask = p->x_vmask;
             an.symflags = p->d_xflags;
@@ -1503,8 +1520,12 @@ static int launch_suite(pqb_panel *p, const Built &full, int64_t b0, int64_t nb,
             // (exclusive: with the whole shared memory of an SM requested, no plain CTA can move in beside a null-aware CTA)
             static const int exclusive = getenv("PQB_COMPACT_EXCLUSIVE") ? atoi(getenv("PQB_COMPACT_EXCLUSIVE")) : 1;
             static const int split0 = getenv("PQB_COMPACT_SPLIT0") ? atoi(getenv("PQB_COMPACT_SPLIT0")) : 1;
+            bool fulls_n = an.gmask == (unsigned)G_ALL && an.nulls_fast && nulls_fulls();
+            for (int k = 0; k < PQB_N_SUITE_OUTPUTS; ++k) fulls_n &= an.out[k] != nullptr;
             auto launch_null = [&](cudaStream_t st) {
-                if (split0 && exclusive)    // (the variant with SMA / EMA / TEMA / MACD over two warps: 288 threads, one CTA per SM)
+                if (fulls_n)                // (exactly the benchmark suite: the compile-time-specialised null-aware kernel)
+                    suite_fused_kernel<true, true><<<(unsigned)n_xb, CTA_THREADS, exclusive ? kMaxSmem : an.smem_bytes, st>>>(an);
+                else if (split0 && exclusive)    // (the variant with SMA / EMA / TEMA / MACD over two warps: 288 threads, one CTA per SM)
                     suite_fused_kernel<false, true, false, true><<<(unsigned)n_xb, CTA_THREADS + 32, kMaxSmem, st>>>(an);
                 else
                     suite_fused_kernel<false, true><<<(unsigned)n_xb, CTA_THREADS, exclusive ? kMaxSmem : an.smem_bytes, st>>>(an);

@@ -289,6 +289,55 @@ def test_a_reused_panel_forgets_the_nulls_of_overwritten_fields():
     p2.close()
 
 
+@pytest.mark.parametrize("seed", range(3))
+def test_null_mode_fast_stages_between_clustered_halts(seed):
+    """Halts come in clusters (a market-wide suspension, a data outage) with hundreds of clean bars between them: stages in which
+    every lane of a block is valid, after `steady_lead` such bars in a row, run the plain steady step inside the null-aware kernel
+    (suite_kernel.cuh run_role "fast stage") and the per-function counters move by whole stages.  Every transition -- slow -> fast
+    after each cluster, fast -> slow at the next one, the delisting tail, a symbol without any null in a flagged block, fields
+    that halt alone -- against the oracle, every symbol, default and random periods."""
+    import polars_quant_b200 as pq
+    from polars_quant_b200 import _native as Nn
+    rng = np.random.default_rng(9100 + seed)
+    S, N = 72, 1500
+    d = synth.ohlcv(S, N, seed=810 + seed)
+    ok = {f: np.ones((S, N), bool) for f in F}
+    clusters = [(290, 330), (771, 779), (1203, 1204)]
+    for s in range(S):
+        if s % 9 == 8:
+            continue                                          # no null at all, in a block whose other lanes have some
+        for lo, hi in clusters:
+            if rng.random() < 0.25:
+                continue
+            a = int(rng.integers(lo, hi)); n = int(rng.integers(1, 6))
+            fields = [F[i] for i in range(4) if rng.random() < 0.4] or [F[int(rng.integers(0, 4))]]
+            for f in fields:
+                ok[f][s, a:a + n] = False
+        if s % 5 == 0:
+            for f in F: ok[f][s, :int(rng.integers(1, 50))] = False      # listed later
+        if s % 13 == 3:
+            for f in F: ok[f][s, N - int(rng.integers(5, 120)):] = False  # delisted
+    P = dict(_DEFAULT_PERIODS)
+    if seed:
+        r = lambda lo, hi: int(rng.integers(lo, hi + 1))
+        fast = r(1, 15)
+        P = dict(sma_period=r(1, 60), ema_period=r(1, 60), tema_period=r(1, 25), trima_period=r(1, 60), bbands_period=r(1, 50),
+                 bbands_nbdevup=1.5, bbands_nbdevdn=2.5, macd_fast=fast, macd_slow=fast + r(1, 20), macd_signal=r(1, 12), rsi_period=r(1, 30),
+                 atr_period=r(1, 30), natr_period=r(1, 30), kdj_fastk=r(1, 40), kdj_slowk=r(1, 8), kdj_slowd=r(1, 8))
+    panel = _panel_with_nulls(pq, d, ok)
+    res = panel.compute(Nn.default_params(**P))
+    for s in range(S):
+        _check_symbol_against_the_oracle(res, s, d, ok, N, P)
+    got = {k: (v[0].copy(), v[1].copy()) for k, v in res.items()}
+    panel.run_host(Nn.default_params(**P), chunk_symbols=32)   # per-block dispatch instead of symbol compaction
+    ref = panel.outputs()
+    for name in pqo.OUTPUT_NAMES:
+        assert np.array_equal(got[name][1], ref[name][1]), name
+        m = ref[name][1]
+        assert np.array_equal(got[name][0][m].view(np.uint64), ref[name][0][m].view(np.uint64)), name
+    panel.close()
+
+
 @pytest.mark.parametrize("seed", range(6))
 def test_null_mode_random_periods_and_null_patterns(seed):
     """Random periods (1 included) x random null patterns: the null-aware walk keeps its per-function rules whatever the window
