@@ -461,8 +461,8 @@ def main():
             cpu = {"value": rate, "unit": UNIT, "cores": used, "kind": "port",
                    "sample": f"{ns} symbols x {N} bars of the same synthetic panel, {reps} passes, C oracle (oracle/pq_oracle.c)"}
         # ---- a realistic panel on the same staging (N = 1 only): 1 % of the symbols with a 3-bar trading halt in close,
-        #      device-resident suite (engine.cu "symbol compaction": the halted symbols run the null-aware kernel in blocks of
-        #      their own beside the plain kernel on every original block) ----
+        #      device-resident suite (engine.cu launch_suite: the blocks that hold a halted symbol run the specialised null-aware kernel
+        #      -- fully valid stages take the plain steady step -- on a second stream beside the plain kernel over the other blocks) ----
         halted = None
         if world == 1 and not args.no_extra:
             try:
@@ -475,8 +475,8 @@ def main():
                 hp.upload()
                 t_h, _, nl_h = hp.time_device(params, warmup=2, iters=5)
                 halted = {"workload": "%d x %d, %d symbols (1 %%) with a 3-bar halt in close, device-resident" % (Se, N, n_h),
-                          "kernel": "compact_kernel + suite_fused_kernel<false,true> (compacted blocks, second stream) || suite_fused_kernel<true,false> "
-                                    "+ compact_kernel + validity", "ms": t_h / 5, "launches": nl_h,
+                          "kernel": "suite_fused_kernel<true,true> (blocks with a halted symbol, second stream) || suite_fused_kernel<true,false> "
+                                    "(the other blocks) + validity", "ms": t_h / 5, "launches": nl_h,
                           "value": Se * N / (t_h / 5 * 1e-3), "unit": UNIT,
                           "vs_clean_panel": (t_h / 5) / (ms_total / args.steps) * (S / Se)}
             except Exception as ex:

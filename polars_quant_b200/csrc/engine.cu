@@ -95,6 +95,8 @@ struct pqb_engine {
     cudaStream_t stream = nullptr;       // compute
     cudaStream_t h2d = nullptr, d2h = nullptr;
     cudaStream_t aux = nullptr;          // the compact tail launch of a small panel runs beside the main launch (launch_suite)
+    cudaStream_t side = nullptr;         // per-block null dispatch: the null-aware launch beside the plain one (which may use `aux` itself)
+    cudaEvent_t ev_side = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_pre = nullptr;
     void *flush_buf = nullptr;
     size_t flush_bytes = 0;
@@ -313,9 +315,11 @@ extern "C" int pqb_engine_create(int device, pqb_engine **out) {
         int least = 0, greatest = 0;
         CU(cudaDeviceGetStreamPriorityRange(&least, &greatest));
         CU(cudaStreamCreateWithPriority(&e->aux, cudaStreamNonBlocking, greatest));
+        CU(cudaStreamCreateWithPriority(&e->side, cudaStreamNonBlocking, greatest));
     }
     CU(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&e->ev_side, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&e->ev_pre, cudaEventDisableTiming));
     CU(cudaStreamCreateWithFlags(&e->d2h, cudaStreamNonBlocking));
     CU(cudaFuncSetAttribute(suite_fused_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
@@ -347,6 +351,8 @@ static void engine_free(pqb_engine *e) {
     if (e->stream) cudaStreamDestroy(e->stream);
     if (e->h2d) cudaStreamDestroy(e->h2d);
     if (e->aux) cudaStreamDestroy(e->aux);
+    if (e->side) cudaStreamDestroy(e->side);
+    if (e->ev_side) cudaEventDestroy(e->ev_side);
     if (e->ev_fork) cudaEventDestroy(e->ev_fork);
     if (e->ev_join) cudaEventDestroy(e->ev_join);
     if (e->ev_pre) cudaEventDestroy(e->ev_pre);
@@ -1482,7 +1488,19 @@ static int launch_suite(pqb_panel *p, const Built &full, int64_t b0, int64_t nb,
             return fail(PQB_ERR_UNSUPPORTED, "midpoint / adosc / mom / roc / cmo / mfi / cci / ... are not built for panels with "
                                              "interior nulls yet (momentum.rs functions fail on such input in the reference)");
         const int *plain_list = nullptr, *null_list = nullptr;
-        did_compact = p->compact && n_null && !go && b0 == 0 && nb == p->n_blocks;
+        // The benchmark suite's null-aware kernel (<FULLS, NULLS> with fast stages) walks a block with a few halted symbols about as fast
+        // as the plain kernel does, so flagged blocks simply run through it, beside the plain launch: no gather, no write-back, no
+        // scattered stores (50,000 x 5,040 with 5 % halted symbols: 22.8 ms compacted).  Symbol compaction stays for the launches that
+        // kernel does not serve (partial suites).  PQB_NULLS_PREFER_DISPATCH=0: compact whenever the panel is prepared for it.
+        static const bool prefer_dispatch = !getenv("PQB_NULLS_PREFER_DISPATCH") || atoi(getenv("PQB_NULLS_PREFER_DISPATCH")) != 0;
+        bool fast_suite = prefer_dispatch && full.a.gmask == (unsigned)G_ALL && nulls_fast_ok(full.a) && nulls_fulls();
+        for (int k = 0; k < PQB_N_SUITE_OUTPUTS; ++k) fast_suite &= full.a.out[k] != nullptr;
+        // ... on a panel of several waves with more than a handful of flagged symbols.  A null-aware CTA that shares its SM with plain CTAs
+        // in the latency regime walks 1.6x slower (8,192 x 5,040 with 83 halted symbols: 3.0 ms dispatched, 2.2 ms compacted onto SMs of
+        // their own), and up to ~64 flagged symbols the gather / write-back is cheaper than a slower block per symbol (20,000 x 5,040:
+        // 20 halted 5.5 ms compacted / 5.8 dispatched, 200 halted 6.2 / 5.2)
+        fast_suite = fast_suite && nb > 3ll * e->sm_count && p->n_x > 64;
+        did_compact = p->compact && n_null && !go && b0 == 0 && nb == p->n_blocks && !fast_suite;
         if (did_compact) {
             // ---- symbol compaction: flagged symbols -> blocks of their own (null-aware kernel, second stream) while the plain
             //      kernel runs every original block; the flagged lanes are overwritten afterwards ----
@@ -1582,10 +1600,10 @@ static int launch_suite(pqb_panel *p, const Built &full, int64_t b0, int64_t nb,
             SuiteArgs an = null_variant(p, full.a);
             if (!an.smem_bytes && (rc = layout_rings(an, p))) return rc;
             CU(cudaEventRecord(e->ev_fork, e->stream));       // (after the block lists' copies)
-            CU(cudaStreamWaitEvent(e->aux, e->ev_fork, 0));
-            std::swap(e->stream, e->aux);                     // (a null-aware launch_one() touches e->stream only)
+            CU(cudaStreamWaitEvent(e->side, e->ev_fork, 0));
+            std::swap(e->stream, e->side);                    // (a null-aware launch_one() touches e->stream only)
             rc = launch_one(an, null_list, n_null);
-            std::swap(e->stream, e->aux);
+            std::swap(e->stream, e->side);
             if (rc) return rc;
             null_done = true;
         }
@@ -1601,8 +1619,8 @@ static int launch_suite(pqb_panel *p, const Built &full, int64_t b0, int64_t nb,
             } else if ((rc = launch_one(full.a, plain_list, nl))) return rc;
         }
         if (null_done) {                                      // join the second stream
-            CU(cudaEventRecord(e->ev_join, e->aux));
-            CU(cudaStreamWaitEvent(e->stream, e->ev_join, 0));
+            CU(cudaEventRecord(e->ev_side, e->side));
+            CU(cudaStreamWaitEvent(e->stream, e->ev_side, 0));
         } else if (!did_compact && n_null) {                  // the flagged blocks: one null-aware launch
             SuiteArgs an = null_variant(p, full.a);
             if (!an.smem_bytes && (rc = layout_rings(an, p))) return rc;

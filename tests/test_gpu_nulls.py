@@ -184,6 +184,26 @@ def test_single_column_calls_with_nulls():
     assert T.compare("sma", *got(), *pqo.sma(c, 10))[0] == 0
 
 
+def _partial_suite_still_compacts(panel, ref):
+    """The full suite sends flagged blocks through its specialised null-aware kernel (per-block dispatch, engine.cu launch_suite);
+    symbol compaction remains the path of every other launch: a partial suite on the same device-resident panel must reproduce
+    the full run's values for the groups it computes (`ref` = the chunked host pipeline's outputs of the full suite)."""
+    from polars_quant_b200 import _native as Nn
+    skip = {"willr", "kdj_k", "kdj_d", "kdj_j"}
+    ref = {k: (v[0].copy(), v[1].copy()) for k, v in ref.items()}
+    panel.upload()
+    panel.run(Nn.default_params(indicators=Nn.IND_ALL & ~(Nn.IND["willr"] | Nn.IND["kdj"])))
+    panel.download()
+    panel.sync()
+    got = panel.outputs()
+    for name in pqo.OUTPUT_NAMES:
+        if name in skip:
+            continue
+        assert np.array_equal(got[name][1], ref[name][1]), name
+        m = ref[name][1]
+        assert np.array_equal(got[name][0][m].view(np.uint64), ref[name][0][m].view(np.uint64)), name
+
+
 def test_symbol_compaction_few_flagged_symbols_in_a_large_panel():
     """A device-resident panel in which FEW symbols need the null-aware kernel (halts, a delisting, a field that starts late)
     and they are spread over many blocks: the engine copies them into blocks of their own, runs the null-aware kernel on those
@@ -221,6 +241,7 @@ def test_symbol_compaction_few_flagged_symbols_in_a_large_panel():
         assert np.array_equal(got[name][1], ref[name][1]), name
         m = ref[name][1]
         assert np.array_equal(got[name][0][m].view(np.uint64), ref[name][0][m].view(np.uint64)), name
+    _partial_suite_still_compacts(panel, ref)
     panel.close()
 
 
@@ -256,6 +277,7 @@ def test_symbol_compaction_direct_mode_many_flagged_symbols():
         assert np.array_equal(got[name][1], ref[name][1]), name
         m = ref[name][1]
         assert np.array_equal(got[name][0][m].view(np.uint64), ref[name][0][m].view(np.uint64)), name
+    _partial_suite_still_compacts(panel, ref)
     panel.close()
 
 
