@@ -1499,7 +1499,12 @@ static int launch_suite(pqb_panel *p, const Built &full, int64_t b0, int64_t nb,
         // in the latency regime walks 1.6x slower (8,192 x 5,040 with 83 halted symbols: 3.0 ms dispatched, 2.2 ms compacted onto SMs of
         // their own), and up to ~64 flagged symbols the gather / write-back is cheaper than a slower block per symbol (20,000 x 5,040:
         // 20 halted 5.5 ms compacted / 5.8 dispatched, 200 halted 6.2 / 5.2)
-        fast_suite = fast_suite && nb > 3ll * e->sm_count && p->n_x > 64;
+        // (beyond 1,024 flagged symbols compaction stores straight into the symbols' lanes -- scattered 8-byte stores, ~0.15 ms per compacted
+        // block: there the dispatch wins on a small panel too; PQB_NULLS_DISPATCH_SMALL_FROM = that count)
+        static const int small_from = getenv("PQB_NULLS_DISPATCH_SMALL_FROM") ? atoi(getenv("PQB_NULLS_DISPATCH_SMALL_FROM")) : 1024;
+        // ... and whenever four blocks out of five hold a flagged symbol anyway (8,192 x 5,040 with 409 halted symbols, one per block or more:
+        // 3.7 ms compacted, 2.25 ms with every block in the null-aware kernel)
+        fast_suite = fast_suite && ((nb > 3ll * e->sm_count && p->n_x > 64) || p->n_x > small_from || n_null * 5 >= nb * 4);
         did_compact = p->compact && n_null && !go && b0 == 0 && nb == p->n_blocks && !fast_suite;
         if (did_compact) {
             // ---- symbol compaction: flagged symbols -> blocks of their own (null-aware kernel, second stream) while the plain
