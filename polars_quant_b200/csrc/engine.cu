@@ -1368,6 +1368,13 @@ static int launch_suite(pqb_panel *p, const Built &full, int64_t b0, int64_t nb,
                     if (waves < best) { best = waves; threads = 32 * W; occ = k; }
                 }
             }
+            // Two-warp CTAs (one slot + the producer): the role warps of the resident CTAs all sat on two of the four SM sub-partitions (ncu, EMA
+            // alone: one scheduler 95 % busy, the next 9 %) -- warp slots go to CTAs in pairs, so CTA j of an SM (blocks sm_count apart) swaps
+            // role and producer warp when (j / 2) is odd (suite_kernel.cuh base_rot).  EMA alone 0.81 -> 0.72 ms (0.85 of peak), RSI 1.86 -> 1.31.
+            // Wider CTAs: every rotation measured was slower (BBANDS, four warps: 1.68 -> 1.80 - 1.98 ms).  PQB_BASE_ROT=0: off
+            static const int rot = getenv("PQB_BASE_ROT") ? atoi(getenv("PQB_BASE_ROT")) : 1;
+            x.base_rot = (rot && x.split_from < 0 && threads == 64) ? e->sm_count : 0;
+            x.base_rot_pair = 1;
             static const bool print_occ = getenv("PQB_PRINT_OCC") != nullptr;
             if (print_occ) {
                 if (!occ) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, threads, (size_t)smem);
