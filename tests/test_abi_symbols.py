@@ -63,6 +63,19 @@ def test_default_params_are_the_reference_python_defaults(lib):
     assert (p.cmo_period, p.mfi_period, p.cci_period) == (14, 14, 14)
 
 
+def test_indicator_bits_of_the_python_mirror_match_the_header():
+    """PQB_IND_* in include/pqb200.h against _native.IND / IND_EXTRA / IND_ALL / IND_FASTK (a Rust host reads the header)."""
+    import re
+    from polars_quant_b200 import _native as N
+    text = (ROOT / "include" / "pqb200.h").read_text()
+    bits = {m.group(1).lower(): 1 << int(m.group(2)) for m in re.finditer(r"PQB_IND_([A-Z]+) = 1u << (\d+)", text)}
+    for name, bit in {**N.IND, **N.IND_EXTRA}.items():
+        assert bits[name] == bit, name
+    assert bits["fastk"] == N.IND_FASTK
+    assert N.IND_ALL == sum(N.IND.values()) == (1 << 15) - 1
+    assert not (N.IND_FASTK & (N.IND_ALL | sum(N.IND_EXTRA.values())))
+
+
 def test_product_never_imports_the_oracle():
     """Only tests/, __graft_entry__.smoke() and bench.py may touch oracle/."""
     for f in (ROOT / "polars_quant_b200").rglob("*"):
